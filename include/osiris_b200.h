@@ -1,0 +1,178 @@
+/*
+ * osiris_b200.h -- C ABI of the B200-native PIC hot path (drop-in boundary for OSIRIS).
+ *
+ * Plain C: pointers, sizes and scalars only.  This is what OSIRIS' Fortran host binds with
+ * ISO_C_BINDING (see INTEGRATION.md for the `bind(c)` interface module and the three
+ * call-site patches).  Every entry point names the reference interface it replaces;
+ * paths are relative to /root/reference/source.
+ *
+ * Conventions (the reference's own, so host arrays can be passed unchanged):
+ *   - particle arrays are the Fortran buffers of t_species (spec/os-spec-define.f03:391-393):
+ *       x(D,np) reals, ix(D,np) int32, p(3,np) reals, q(np) reals; component fastest;
+ *       ix is the 1-based local cell, x in [-0.5,0.5) relative to it;
+ *   - grids are t_vdf buffers (vdf/os-vdf-define.f03:345-351): f(3, S1, S2[, S3]),
+ *       S_d = nx_d + gc[0][d] + gc[1][d], cell 1 at padded position gc[0][d];
+ *   - "real" is float when real_bytes == 4 and double when 8 (p_k_part == p_k_fld);
+ *   - all functions return 0 on success or a negative OSGPU_ERR_* code; the text of the last
+ *     error is available from osgpu_last_error().  The Fortran shim turns a non-zero status
+ *     into ERROR()/abort_program(p_err_invalid) (system/os-sys-multi.f03:1203-1240).
+ *   - one host thread drives one GPU (n_threads must be 1 for push_type = "cuda").
+ */
+#ifndef OSIRIS_B200_H
+#define OSIRIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSGPU_OK 0
+#define OSGPU_ERR_INVALID -1     /* bad argument / unsupported configuration          */
+#define OSGPU_ERR_CUDA -2        /* CUDA runtime or driver error                      */
+#define OSGPU_ERR_NCCL -3        /* NCCL error                                        */
+#define OSGPU_ERR_CAPACITY -4    /* particle / mover buffer too small                 */
+#define OSGPU_ERR_STABILITY -5   /* Courant condition violated (test_stability_yee)   */
+#define OSGPU_ERR_NO_DEVICE -6   /* no CUDA device: there is no CPU fallback          */
+
+#define OSGPU_MAX_DIM 3
+#define OSGPU_NCCL_ID_BYTES 128
+
+typedef struct osgpu_sim osgpu_sim; /* opaque: owns every device buffer */
+
+/* Everything init needs; mirrors what init_sim hands to emf/jay/part
+ * (os-simulation.f03:232-400) and t_node_conf (os-nconf.f03:45-107). */
+typedef struct osgpu_config {
+  int32_t dim;        /* p_x_dim: 2 or 3 (os-param.f90:20)                               */
+  int32_t order;      /* particles{interpolation}: 1 linear .. 4 quartic                 */
+  int32_t real_bytes; /* 4 | 8 (PRECISION_SINGLE|DOUBLE, os-param.f90:27-55)             */
+  int32_t nspecies;   /* number of t_species                                             */
+  int32_t nx[OSGPU_MAX_DIM];        /* local cells my_nx(3,:) (grid/os-grid-define.f03)  */
+  int32_t gc_emf[2][OSGPU_MAX_DIM]; /* guard cells of the host E/B arrays [lower|upper]  */
+  int32_t gc_jay[2][OSGPU_MAX_DIM]; /* guard cells of the host J array                   */
+  double dx[OSGPU_MAX_DIM];         /* cell size                                         */
+  double dt;                        /* time step (full double; particles round it)       */
+  /* domain decomposition: node_conf{node_number, if_periodic} (os-nconf.f03:222)        */
+  int32_t node_dims[OSGPU_MAX_DIM];   /* ranks per axis (1,1,1 on a single GPU)          */
+  int32_t node_coords[OSGPU_MAX_DIM]; /* this rank's cartesian coordinates               */
+  int32_t periodic[OSGPU_MAX_DIM];    /* periodic axes                                   */
+  int32_t rank;       /* NCCL rank = cartesian rank, x fastest (mpi_cart_create order is */
+  int32_t nranks;     /* reproduced by osgpu_cart_rank)                                  */
+  int32_t device;     /* CUDA device ordinal, -1 = rank % device_count                   */
+  int32_t smooth_order; /* current smoothing passes folded into gc (0 = none)            */
+  int32_t reserved[7];
+} osgpu_config;
+
+/* ---- library / topology helpers (no GPU needed) -------------------------------------- */
+const char *osgpu_version(void);
+const char *osgpu_last_error(void);
+int osgpu_device_count(void);
+/* cartesian rank <-> coords, x fastest; neighbour(2,D) of t_node_conf (os-nconf.f03:1101-1112):
+ * neighbors[2*d+0] = lower, [2*d+1] = upper, -1 where there is none */
+int osgpu_cart_rank(int dim, const int32_t *dims, const int32_t *coords);
+int osgpu_cart_coords(int dim, const int32_t *dims, int rank, int32_t *coords);
+int osgpu_cart_neighbors(int dim, const int32_t *dims, const int32_t *periodic, int rank,
+                         int32_t *neighbors);
+/* guard-cell exchange ranges along `axis` (vdf/os-vdf-comm.f90:756-784, 866-894), cell indices
+ * inclusive.  mode 0 = replace (E,B), 1 = add (J).  out = {send_lo0, send_lo1, send_up0, send_up1,
+ * recv_lo0, recv_lo1, recv_up0, recv_up1} */
+int osgpu_exchange_ranges(int nx, int gcl, int gcu, int mode, int32_t *out8);
+/* minimum guard cells the particles need for an interpolation order
+ * (particles/os-particles.f03:329-346) merged with the Yee solver's (1,2)
+ * (emf/solver/os-emf-solver-yee.f03:458-468): out = {lower, upper} */
+int osgpu_min_gc(int order, int32_t *out2);
+/* 16-byte NCCL unique id for osgpu_init; rank 0 creates it, the host broadcasts it (MPI_Bcast
+ * in OSIRIS, torch.distributed in bench.py) */
+int osgpu_nccl_unique_id(void *id_bytes /* OSGPU_NCCL_ID_BYTES */);
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* replaces: init of t_emf/t_current/t_particles device mirrors (os-simulation.f03:232-400) */
+int osgpu_init(osgpu_sim **sim, const osgpu_config *cfg, const void *nccl_id /* or NULL */);
+int osgpu_finalize(osgpu_sim *sim);
+
+/* ---- species: t_species buffers -------------------------------------------------------- */
+/* replaces: alloc of t_species buffers (spec/os-spec-define.f03:1420-1468).  np_max bounds the
+ * particles this rank can hold (num_par_max). */
+int osgpu_species_create(osgpu_sim *sim, int sp_id, double rqm, int64_t np_max);
+/* host AoS -> device tile-binned SoA.  tag may be NULL (then tag = 0-based index).
+ * replaces nothing in the reference: it is the H2D half of the fill_data contract
+ * (spec/os-species.f03:1867-1894). */
+int osgpu_species_upload(osgpu_sim *sim, int sp_id, int64_t np, const int32_t *ix, const void *x,
+                         const void *p, const void *q, const int64_t *tag);
+int64_t osgpu_species_count(osgpu_sim *sim, int sp_id);
+/* device -> host AoS (fill_data target).  Arrays hold osgpu_species_count() particles, in device
+ * (tile) order; tag (may be NULL) identifies them. */
+int osgpu_species_download(osgpu_sim *sim, int sp_id, int32_t *ix, void *x, void *p, void *q,
+                           int64_t *tag);
+
+/* ---- fields: t_emf%e, t_emf%b, t_current%pf(1) ------------------------------------------ */
+int osgpu_fields_upload(osgpu_sim *sim, const void *e, const void *b);
+int osgpu_fields_download(osgpu_sim *sim, void *e, void *b);     /* emf/os-emf.f03:1158-1184 */
+int osgpu_current_upload(osgpu_sim *sim, const void *j);
+int osgpu_current_download(osgpu_sim *sim, void *j); /* current/os-current-define.f03:734-757 */
+
+/* ---- the time step and its phases ------------------------------------------------------- */
+/* One call = the hot part of iter_sim (os-simulation.f03:561-661), nsteps times:
+ *   emf%update_boundary -> part%advance_deposit -> part%update_boundary -> (sort) ->
+ *   jay%update_boundary -> emf%advance.
+ * ene_kin[nspecies] (may be NULL) receives, for the LAST step, sum(q*u^2/(gamma+1)) per species
+ * (time-centred, spec/os-spec-push.f03:500); multiply by rqm*prod(dx) for HIST/par_ene. */
+int osgpu_step(osgpu_sim *sim, int nsteps, double *ene_kin);
+/* the phases, individually (parity tests call these one at a time) */
+int osgpu_emf_update_boundary(osgpu_sim *sim);     /* emf/boundary/os-emf-boundary.f90:723-830 */
+int osgpu_advance_deposit(osgpu_sim *sim, double *ene_kin); /* particles/os-particles.f03:1362 */
+int osgpu_particles_update_boundary(osgpu_sim *sim); /* spec/os-spec-boundary.f03:1099-1232   */
+int osgpu_sort(osgpu_sim *sim);                      /* spec/os-species.f03:269-332           */
+int osgpu_current_update_boundary(osgpu_sim *sim); /* current/os-current-define.f03:683-727 */
+int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-482 (Yee)   */
+/* field energy per component, interior cells: out6 = {E1,E2,E3,B1,B2,B3}
+ * (emf/diagnostics/os-emf-diagnostics.f03:43-58); summed over this rank only */
+int osgpu_field_energy(osgpu_sim *sim, double *out6);
+/* device-timed duration (ms) of each phase of the last osgpu_step call, summed over its steps:
+ * {emf_bnd, push_deposit, part_bnd, jay_bnd, solver, total}; feeds the m_logprof events
+ * 'update emf boundary', 'advance deposit', 'update particle boundary', 'update current
+ * boundary', 'field solver' (os-logprof.f90:146-260). */
+int osgpu_phase_times_ms(osgpu_sim *sim, double *out6);
+/* number of kernel launches issued by this handle so far */
+int64_t osgpu_launch_count(osgpu_sim *sim);
+/* cudaStream_t the handle launches on (for CUDA-event timing by the caller) */
+void *osgpu_stream(osgpu_sim *sim);
+
+/* ---- stateless pushers with EXACTLY the reference C signature --------------------------- */
+/* replace: vadvance_deposit_{2d,3d}_s{1..4}_ (simd/os-spec-push-avx2.c:471-476, 1141-1145;
+ * call sites spec/os-spec-vpush.f03:152-155, 294-297).  Host arrays in, host arrays out:
+ * x, ix, u are advanced in place for particles i0..i1 (1-based, inclusive), the current is
+ * ACCUMULATED into j and the time-centred energy into *ene, as the reference does.
+ * Single precision: osgpu_vadvance_deposit_*; double: osgpu_vadvance_deposit_*_d.
+ * On failure they print the error and exit(1), like the reference (:1213-1216). */
+#define OSGPU_DECL_VADV(name, real)                                                            \
+  void name(int *ix, real *x, real *u, real *q, int *i0, int *i1, real *rqm, real *efield,     \
+            real *bfield, int *emf_size, int *emf_offset, real *j, int *j_size, int *j_offset, \
+            double *dx, double *dt, double *ene)
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s1, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s2, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s3, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s4, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s1, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s2, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s3, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s4, float);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s1_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s2_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s3_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_2d_s4_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s1_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s2_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s3_d, double);
+OSGPU_DECL_VADV(osgpu_vadvance_deposit_3d_s4_d, double);
+/* generic form of the above (dim, order, precision at run time); returns a status instead of
+ * exiting.  i0, i1 1-based inclusive. */
+int osgpu_vadvance_deposit(int dim, int order, int real_bytes, int *ix, void *x, void *u, void *q,
+                           int i0, int i1, double rqm, const void *efield, const void *bfield,
+                           const int *emf_size, const int *emf_offset, void *j, const int *j_size,
+                           const int *j_offset, const double *dx, double dt, double *ene);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSIRIS_B200_H */

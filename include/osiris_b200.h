@@ -21,6 +21,7 @@
 #ifndef OSIRIS_B200_H
 #define OSIRIS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -137,6 +138,11 @@ int osgpu_phase_times_ms(osgpu_sim *sim, double *out6);
 int64_t osgpu_launch_count(osgpu_sim *sim);
 /* cudaStream_t the handle launches on (for CUDA-event timing by the caller) */
 void *osgpu_stream(osgpu_sim *sim);
+int osgpu_sync(osgpu_sim *sim);
+/* page-locked host memory for arrays that cross the boundary every step (the Fortran side can
+ * c_f_pointer these); plain pageable arrays work too, at pageable-copy speed */
+void *osgpu_host_alloc(size_t bytes);
+void osgpu_host_free(void *p);
 
 /* ---- stateless pushers with EXACTLY the reference C signature --------------------------- */
 /* replace: vadvance_deposit_{2d,3d}_s{1..4}_ (simd/os-spec-push-avx2.c:471-476, 1141-1145;

@@ -1,0 +1,294 @@
+// fields.cu -- grid kernels: Yee FDTD advance, guard-cell updates (periodic in-rank copy/fold and
+// slab pack/unpack for the NCCL exchange), host<->device layout conversion, field energy.
+//
+// Reference: source/emf/solver/os-emf-solver-yee.f03:102-138, 211-251, 287-326, 385-428, 542-568;
+// source/vdf/os-vdf-comm.f90:142-326 (periodic), :332-473 (pack/unpack), :756-784 (ranges);
+// source/emf/diagnostics/os-emf-diagnostics.f03:43-58 (energy).
+//
+// All arithmetic is written as separate multiplies and adds in the reference's order (the unit is
+// compiled with -fmad=false), so E and B are bit-identical to the Fortran statement.
+#include "common.cuh"
+#include "fields.cuh"
+
+namespace osgpu {
+
+// ---------------------------------------------------------------------------------------------
+// Yee: B -= dt * curl E over cells 0..nx+1 (dbdt_2d/3d_yee)
+// ---------------------------------------------------------------------------------------------
+template <int DIM, typename T>
+__global__ void __launch_bounds__(128) yee_b_kernel(Field3<T> b, Field3<const T> e, Grid g, T dtdx1,
+                                                    T dtdx2, T dtdx3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // cell index 0..nx+1
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i > g.nx[0] + 1) return;
+  const long long sy = g.P0, sz = (long long)g.P0 * g.S[1];
+  const long long c =
+      g.at(i - 1 + g.gl[0], j - 1 + g.gl[1], (DIM == 3) ? k - 1 + g.gl[2] : 0);
+  const T e1 = e.c[0][c], e2 = e.c[1][c], e3 = e.c[2][c];
+  if (DIM == 2) {
+    b.c[0][c] = b.c[0][c] - dtdx2 * (e.c[2][c + sy] - e3);
+    b.c[1][c] = b.c[1][c] + dtdx1 * (e.c[2][c + 1] - e3);
+    b.c[2][c] = b.c[2][c] - dtdx1 * (e.c[1][c + 1] - e2) + dtdx2 * (e.c[0][c + sy] - e1);
+  } else {
+    b.c[0][c] = b.c[0][c] - dtdx2 * (e.c[2][c + sy] - e3) + dtdx3 * (e.c[1][c + sz] - e2);
+    b.c[1][c] = b.c[1][c] + dtdx1 * (e.c[2][c + 1] - e3) - dtdx3 * (e.c[0][c + sz] - e1);
+    b.c[2][c] = b.c[2][c] - dtdx1 * (e.c[1][c + 1] - e2) + dtdx2 * (e.c[0][c + sy] - e1);
+  }
+}
+
+// Yee: E += dt * (curl B - J) over cells 1..nx+1 (dedt_2d/3d_yee)
+template <int DIM, typename T>
+__global__ void __launch_bounds__(128)
+    yee_e_kernel(Field3<T> e, Field3<const T> b, Field3<const T> jay, Grid g, T dtdx1, T dtdx2,
+                 T dtdx3, T dtif) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;  // cell index 1..nx+1
+  const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+  if (i > g.nx[0] + 1) return;
+  const long long sy = g.P0, sz = (long long)g.P0 * g.S[1];
+  const long long c =
+      g.at(i - 1 + g.gl[0], j - 1 + g.gl[1], (DIM == 3) ? k - 1 + g.gl[2] : 0);
+  const T b1 = b.c[0][c], b2 = b.c[1][c], b3 = b.c[2][c];
+  if (DIM == 2) {
+    e.c[0][c] = e.c[0][c] - dtif * jay.c[0][c] + dtdx2 * (b3 - b.c[2][c - sy]);
+    e.c[1][c] = e.c[1][c] - dtif * jay.c[1][c] - dtdx1 * (b3 - b.c[2][c - 1]);
+    e.c[2][c] = e.c[2][c] - dtif * jay.c[2][c] + dtdx1 * (b2 - b.c[1][c - 1]) -
+                dtdx2 * (b1 - b.c[0][c - sy]);
+  } else {
+    e.c[0][c] = e.c[0][c] - dtif * jay.c[0][c] + dtdx2 * (b3 - b.c[2][c - sy]) -
+                dtdx3 * (b2 - b.c[1][c - sz]);
+    e.c[1][c] = e.c[1][c] - dtif * jay.c[1][c] + dtdx3 * (b1 - b.c[0][c - sz]) -
+                dtdx1 * (b3 - b.c[2][c - 1]);
+    e.c[2][c] = e.c[2][c] - dtif * jay.c[2][c] + dtdx1 * (b2 - b.c[1][c - 1]) -
+                dtdx2 * (b1 - b.c[0][c - sy]);
+  }
+}
+
+template <typename T>
+int yee_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+                cudaStream_t st, long long *launches) {
+  // advance_yee: B half step, E full step, B half step (os-emf-solver-yee.f03:542-568);
+  // dtdx = real(dt/dx, p_k_fld) with the full-precision dt (:223-225, :398-401)
+  const double dtb = dt / 2.0;
+  const T hb1 = (T)(dtb / dx[0]), hb2 = (T)(dtb / dx[1]), hb3 = (g.dim == 3) ? (T)(dtb / dx[2]) : T(0);
+  const T he1 = (T)(dt / dx[0]), he2 = (T)(dt / dx[1]), he3 = (g.dim == 3) ? (T)(dt / dx[2]) : T(0);
+  const T dtif = (T)dt;
+  Field3<const T> ce{{e.c[0], e.c[1], e.c[2]}}, cb{{b.c[0], b.c[1], b.c[2]}},
+      cj{{jay.c[0], jay.c[1], jay.c[2]}};
+  const dim3 blk(128);
+  const dim3 gb((g.nx[0] + 2 + 127) / 128, g.nx[1] + 2, g.dim == 3 ? g.nx[2] + 2 : 1);
+  const dim3 ge((g.nx[0] + 1 + 127) / 128, g.nx[1] + 1, g.dim == 3 ? g.nx[2] + 1 : 1);
+  if (g.dim == 2) {
+    yee_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+    yee_e_kernel<2, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif);
+    yee_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+  } else {
+    yee_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+    yee_e_kernel<3, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif);
+    yee_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+  }
+  *launches += 3;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int yee_advance<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>,
+                                const double *, double, cudaStream_t, long long *);
+template int yee_advance<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>,
+                                 const double *, double, cudaStream_t, long long *);
+
+// ---------------------------------------------------------------------------------------------
+// Slab helpers.  A slab is the padded range [a0, a1] along `axis` times the full padded extent of
+// the other axes (that is how update_boundary_vdf propagates edges and corners, os-vdf-comm.f90
+// :686-719).  r enumerates the slab with the x index fastest.
+// ---------------------------------------------------------------------------------------------
+struct Slab {
+  int axis, a0, ext[3];
+  long long vol;
+};
+static Slab make_slab(const Grid &g, int axis, int a0, int a1) {
+  Slab s;
+  s.axis = axis;
+  s.a0 = a0;
+  for (int d = 0; d < 3; d++) s.ext[d] = g.S[d];
+  s.ext[axis] = a1 - a0 + 1;
+  s.vol = (long long)s.ext[0] * s.ext[1] * s.ext[2];
+  return s;
+}
+__device__ __forceinline__ long long slab_at(const Slab &s, const Grid &g, long long r) {
+  int i[3];
+  i[0] = (int)(r % s.ext[0]); r /= s.ext[0];
+  i[1] = (int)(r % s.ext[1]);
+  i[2] = (int)(r / s.ext[1]);
+  i[s.axis] += s.a0;
+  return g.at(i[0], i[1], i[2]);
+}
+
+template <typename T, int NC> struct Comps {
+  T *c[NC];
+};
+
+// in-rank periodic update along one axis (update_periodic_vdf): mode 0 copies the opposite
+// interior cells into the guard cells, mode 1 stores guard + image in both places.
+template <typename T, int NC>
+__global__ void __launch_bounds__(256)
+    periodic_kernel(Comps<T, NC> f, Grid g, Slab lo, Slab up, long long shift, int mode) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r < lo.vol) {
+    const long long p = slab_at(lo, g, r);
+    if (mode == 0) f.c[c][p] = f.c[c][p + shift];
+    else { const T v = f.c[c][p] + f.c[c][p + shift]; f.c[c][p] = v; f.c[c][p + shift] = v; }
+  } else if (r < lo.vol + up.vol) {
+    const long long p = slab_at(up, g, r - lo.vol);
+    if (mode == 0) f.c[c][p] = f.c[c][p - shift];
+    else { const T v = f.c[c][p] + f.c[c][p - shift]; f.c[c][p - shift] = v; f.c[c][p] = v; }
+  }
+}
+
+template <typename T>
+int periodic_update(const Grid &g, T *const *comps, int ncomp, int axis, int mode, cudaStream_t st,
+                    long long *launches) {
+  if (g.nx[axis] < g.gl[axis] + g.gu[axis]) {
+    set_error("periodic guard update needs nx >= gc_lower + gc_upper on axis %d", axis);
+    return OSGPU_ERR_INVALID;
+  }
+  // lower guards: cells 1-gl..0 -> padded 0..gl-1; upper guards: cells nx+1..nx+gu
+  const Slab lo = make_slab(g, axis, 0, g.gl[axis] - 1);
+  const Slab up = make_slab(g, axis, g.nx[axis] + g.gl[axis], g.S[axis] - 1);
+  long long stride = 1;
+  if (axis == 1) stride = g.P0;
+  if (axis == 2) stride = (long long)g.P0 * g.S[1];
+  const long long shift = stride * g.nx[axis];
+  const long long tot = lo.vol + up.vol;
+  if (tot == 0) return OSGPU_OK;
+  const dim3 grid((unsigned)((tot + 255) / 256), ncomp);
+  if (ncomp == 6) {
+    Comps<T, 6> f;
+    for (int c = 0; c < 6; c++) f.c[c] = comps[c];
+    periodic_kernel<T, 6><<<grid, 256, 0, st>>>(f, g, lo, up, shift, mode);
+  } else {
+    Comps<T, 3> f;
+    for (int c = 0; c < 3; c++) f.c[c] = comps[c];
+    periodic_kernel<T, 3><<<grid, 256, 0, st>>>(f, g, lo, up, shift, mode);
+  }
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int periodic_update<float>(const Grid &, float *const *, int, int, int, cudaStream_t, long long *);
+template int periodic_update<double>(const Grid &, double *const *, int, int, int, cudaStream_t, long long *);
+
+// pack / unpack a slab of all components into / from a contiguous message buffer
+// (pack_vdf / unpack_vdf / unpack_add_vdf, os-vdf-comm.f90:332-473)
+template <typename T, int NC>
+__global__ void __launch_bounds__(256) pack_kernel(Comps<T, NC> f, Grid g, Slab s, T *buf, int dir) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (r >= s.vol) return;
+  const long long p = slab_at(s, g, r);
+  T *m = buf + c * s.vol + r;
+  if (dir == 0) *m = f.c[c][p];          // pack
+  else if (dir == 1) f.c[c][p] = *m;     // unpack, replace
+  else f.c[c][p] = f.c[c][p] + *m;       // unpack, add
+}
+
+template <typename T>
+int slab_copy(const Grid &g, T *const *comps, int ncomp, int axis, int a0, int a1, T *buf, int dir,
+              cudaStream_t st, long long *launches) {
+  const Slab s = make_slab(g, axis, a0, a1);
+  if (s.vol <= 0) return OSGPU_OK;
+  const dim3 grid((unsigned)((s.vol + 255) / 256), ncomp);
+  if (ncomp == 6) {
+    Comps<T, 6> f;
+    for (int c = 0; c < 6; c++) f.c[c] = comps[c];
+    pack_kernel<T, 6><<<grid, 256, 0, st>>>(f, g, s, buf, dir);
+  } else {
+    Comps<T, 3> f;
+    for (int c = 0; c < 3; c++) f.c[c] = comps[c];
+    pack_kernel<T, 3><<<grid, 256, 0, st>>>(f, g, s, buf, dir);
+  }
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int slab_copy<float>(const Grid &, float *const *, int, int, int, int, float *, int, cudaStream_t, long long *);
+template int slab_copy<double>(const Grid &, double *const *, int, int, int, int, double *, int, cudaStream_t, long long *);
+
+long long slab_volume(const Grid &g, int axis, int a0, int a1) {
+  long long v = a1 - a0 + 1;
+  for (int d = 0; d < 3; d++)
+    if (d != axis) v *= g.S[d];
+  return v < 0 ? 0 : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host t_vdf layout f(3, S1h, S2h, S3h) (component fastest, its own guard cells) <-> device planes
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+    layout_kernel(Field3<T> f, Grid g, T *aos, int hs0, int hs1, int hs2, int hg0, int hg1, int hg2,
+                  int to_device) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long hvol = (long long)hs0 * hs1 * hs2;
+  if (r >= hvol) return;
+  const int i0 = (int)(r % hs0), i1 = (int)((r / hs0) % hs1), i2 = (int)(r / ((long long)hs0 * hs1));
+  // host padded coordinate -> device padded coordinate
+  const long long p = g.at(i0 - hg0 + g.gl[0], i1 - hg1 + g.gl[1], (g.dim == 3) ? i2 - hg2 + g.gl[2] : 0);
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    if (to_device) f.c[c][p] = aos[3 * r + c];
+    else aos[3 * r + c] = f.c[c][p];
+  }
+}
+template <typename T>
+int layout_convert(const Grid &g, Field3<T> f, T *aos, const int *hsize, const int *hgc, int to_device,
+                   cudaStream_t st, long long *launches) {
+  const long long hvol = (long long)hsize[0] * hsize[1] * hsize[2];
+  layout_kernel<T><<<(unsigned)((hvol + 255) / 256), 256, 0, st>>>(f, g, aos, hsize[0], hsize[1], hsize[2],
+                                                                   hgc[0], hgc[1], hgc[2], to_device);
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int layout_convert<float>(const Grid &, Field3<float>, float *, const int *, const int *, int, cudaStream_t, long long *);
+template int layout_convert<double>(const Grid &, Field3<double>, double *, const int *, const int *, int, cudaStream_t, long long *);
+
+// ---------------------------------------------------------------------------------------------
+// field energy: sum over interior cells of f_c^2, double accumulation
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) energy_kernel(Comps<T, 6> f, Grid g, double *out6) {
+  const int c = blockIdx.y;
+  const long long ncell = (long long)g.nx[0] * g.nx[1] * g.nx[2];
+  double acc = 0.0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < ncell;
+       r += (long long)gridDim.x * blockDim.x) {
+    const int i0 = (int)(r % g.nx[0]), i1 = (int)((r / g.nx[0]) % g.nx[1]);
+    const int i2 = (int)(r / ((long long)g.nx[0] * g.nx[1]));
+    const double v = (double)f.c[c][g.at(i0 + g.gl[0], i1 + g.gl[1], (g.dim == 3) ? i2 + g.gl[2] : 0)];
+    acc += v * v;
+  }
+  __shared__ double s[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; w++) t += s[w];
+    atomicAdd(&out6[c], t);
+  }
+}
+template <typename T>
+int field_energy(const Grid &g, T *const *comps6, double *dev_out6, cudaStream_t st, long long *launches) {
+  Comps<T, 6> f;
+  for (int c = 0; c < 6; c++) f.c[c] = comps6[c];
+  OSGPU_CUDA(cudaMemsetAsync(dev_out6, 0, 6 * sizeof(double), st));
+  energy_kernel<T><<<dim3(296, 6), 256, 0, st>>>(f, g, dev_out6);
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int field_energy<float>(const Grid &, float *const *, double *, cudaStream_t, long long *);
+template int field_energy<double>(const Grid &, double *const *, double *, cudaStream_t, long long *);
+
+}  // namespace osgpu

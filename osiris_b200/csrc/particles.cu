@@ -1,0 +1,352 @@
+// particles.cu -- particle bookkeeping kernels: tile binning (upload / counting sort by tile),
+// re-insertion of particles that changed tile, periodic wrap, migration pack/unpack, download.
+//
+// Reference counterparts: sort_species / generate_sort_idx / rearrange_species
+// (source/spec/os-species.f03:269-702), update_boundary_species and helpers
+// (source/spec/os-spec-boundary.f03:538-816, 1099-1290), pack/unpack of migrating particles
+// (source/spec/os-spec-comm.f90:309-759).  The reference re-sorts by cell every n_sort steps and
+// scans every particle for boundary crossings each step; here particles are kept binned by cell
+// tile at all times and only the particles that left their tile are touched.
+#include "common.cuh"
+#include "particles.cuh"
+
+namespace osgpu {
+
+using namespace pic;
+
+constexpr int GRID_STRIDE_BLOCKS = 148 * 8;
+
+// tile index and packed tile-local cell of a 1-based local cell index
+__device__ __forceinline__ bool locate(const int *ix, int dim, const Tiling &tl, const int *nx,
+                                       int *tile, int *cell) {
+  int t = 0, mul = 1, c = 0;
+  bool ok = true;
+  for (int d = 0; d < 3; d++) {
+    int i0 = (d < dim) ? ix[d] - 1 : 0;
+    ok &= (i0 >= 0) && (i0 < ((d < dim) ? nx[d] : 1));
+    const int td = i0 / tl.T[d];
+    t += mul * td;
+    mul *= tl.nt[d];
+    c |= (i0 - td * tl.T[d] + 1) << (d * CELL_BITS);
+  }
+  *tile = t;
+  *cell = c;
+  return ok;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    count_kernel(AosParticles<T> in, long long np, int dim, Tiling tl, Grid g, int *tile_cnt, int *errflag) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ix[3] = {1, 1, 1};
+    for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d];
+    int t, c;
+    if (locate(ix, dim, tl, g.nx, &t, &c)) atomicAdd(&tile_cnt[t], 1);
+    else atomicOr(errflag, ERRF_BAD_CELL);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    scatter_kernel(AosParticles<T> in, long long np, long long tag_base, int dim, Tiling tl, Grid g,
+                   const int *tile_off, int *cursor, SpeciesView<T> sp) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ix[3] = {1, 1, 1};
+    for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d];
+    int t, c;
+    if (!locate(ix, dim, tl, g.nx, &t, &c)) continue;
+    const long long s = (long long)tile_off[t] + atomicAdd(&cursor[t], 1);
+    for (int d = 0; d < dim; d++) sp.x[d][s] = in.x[dim * i + d];
+    for (int d = 0; d < 3; d++) sp.p[d][s] = in.p[3 * i + d];
+    sp.q[s] = in.q[i];
+    sp.cell[s] = c;
+    sp.tag[s] = in.tag ? in.tag[i] : tag_base + i;
+  }
+}
+
+// one CTA per tile: live slots -> AoS output rows out_off[tile] ...
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gather_kernel(SpeciesView<T> sp, const int *tile_off, const int *tile_cnt, const long long *out_off,
+                  int dim, Tiling tl, int *oix, T *ox, T *op, T *oq, long long *otag, int by_tag) {
+  const int tile = blockIdx.x;
+  const int n = tile_cnt[tile];
+  const long long off = tile_off[tile], o = out_off[tile];
+  int tc[3], t = tile;
+  tc[0] = t % tl.nt[0]; t /= tl.nt[0];
+  tc[1] = t % tl.nt[1];
+  tc[2] = t / tl.nt[1];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long s = off + i, r = by_tag ? sp.tag[s] : o + i;
+    const int cell = sp.cell[s];
+    for (int d = 0; d < dim; d++) {
+      ox[dim * r + d] = sp.x[d][s];
+      oix[dim * r + d] = tc[d] * tl.T[d] + cell_l(cell, d) + 1;
+    }
+    for (int d = 0; d < 3; d++) op[3 * r + d] = sp.p[d][s];
+    oq[r] = sp.q[s];
+    if (otag) otag[r] = sp.tag[s];
+  }
+}
+
+// pending movers (not yet re-inserted, e.g. after a bare advance_deposit) -> AoS output rows
+template <typename T>
+__global__ void __launch_bounds__(256)
+    mover_gather_kernel(MoverView<T> mv, long long out_base, int dim, int *oix, T *ox, T *op, T *oq,
+                        long long *otag, int by_tag) {
+  const int n = min(*mv.count, mv.cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const long long r = by_tag ? mv.tag[i] : out_base + i;
+    for (int d = 0; d < dim; d++) {
+      ox[dim * r + d] = mv.x[d][i];
+      oix[dim * r + d] = mv.ix[d][i];
+    }
+    for (int d = 0; d < 3; d++) op[3 * r + d] = mv.p[d][i];
+    oq[r] = mv.q[i];
+    if (otag) otag[r] = mv.tag[i];
+  }
+}
+
+// Movers: wrap the axes on which this rank is its own periodic neighbour
+// (spec/os-spec-boundary.f03:1280-1290), then count arrivals per destination tile.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    route_kernel(MoverView<T> mv, int dim, Tiling tl, Grid g, int wrap0, int wrap1, int wrap2, int *tile_arr,
+                 int *errflag) {
+  const int n = min(*mv.count, mv.cap);
+  const int wrap[3] = {wrap0, wrap1, wrap2};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int ix[3] = {1, 1, 1};
+    if (mv.ix[0][i] == INT_MIN) continue;  // sent to another rank
+    for (int d = 0; d < dim; d++) {
+      int v = mv.ix[d][i];
+      if (wrap[d]) {
+        if (v < 1) v += g.nx[d];
+        else if (v > g.nx[d]) v -= g.nx[d];
+        mv.ix[d][i] = v;
+      }
+      ix[d] = v;
+    }
+    int t, c;
+    if (locate(ix, dim, tl, g.nx, &t, &c)) atomicAdd(&tile_arr[t], 1);
+    else atomicOr(errflag, ERRF_BAD_CELL);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    capacity_kernel(const int *tile_off, const int *tile_cnt, const int *tile_arr, int ntile, int *errflag) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ntile && tile_cnt[t] + tile_arr[t] > tile_off[t + 1] - tile_off[t]) atomicOr(errflag, ERRF_TILE_OVERFLOW);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    insert_kernel(MoverView<T> mv, int dim, Tiling tl, Grid g, const int *tile_off, int *tile_cnt,
+                  SpeciesView<T> sp) {
+  const int n = min(*mv.count, mv.cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (mv.ix[0][i] == INT_MIN) continue;
+    int ix[3] = {1, 1, 1};
+    for (int d = 0; d < dim; d++) ix[d] = mv.ix[d][i];
+    int t, c;
+    if (!locate(ix, dim, tl, g.nx, &t, &c)) continue;
+    const long long s = (long long)tile_off[t] + atomicAdd(&tile_cnt[t], 1);
+    for (int d = 0; d < dim; d++) sp.x[d][s] = mv.x[d][i];
+    for (int d = 0; d < 3; d++) sp.p[d][s] = mv.p[d][i];
+    sp.q[s] = mv.q[i];
+    sp.cell[s] = c;
+    sp.tag[s] = mv.tag[i];
+  }
+}
+
+// one CTA per tile: copy the live range into the new layout (counting sort by tile, out of place
+// like rearrange_species, os-species.f03:512-702)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    relayout_kernel(SpeciesView<T> src, const int *old_off, const int *tile_cnt, SpeciesView<T> dst,
+                    const int *new_off, int dim) {
+  const int tile = blockIdx.x;
+  const int n = tile_cnt[tile];
+  const long long so = old_off[tile], dn = new_off[tile];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int d = 0; d < dim; d++) dst.x[d][dn + i] = src.x[d][so + i];
+    for (int d = 0; d < 3; d++) dst.p[d][dn + i] = src.p[d][so + i];
+    dst.q[dn + i] = src.q[so + i];
+    dst.cell[dn + i] = src.cell[so + i];
+    dst.tag[dn + i] = src.tag[so + i];
+  }
+}
+
+// ---- migration -------------------------------------------------------------------------------
+// wire record (32-bit words): [tag lo, tag hi][reals: x(D) p(3) q][ix(D)][pad to even]
+template <typename T> __host__ __device__ inline int rec_words(int dim) {
+  const int w = 2 + (dim + 4) * (int)(sizeof(T) / 4) + dim;
+  return (w + 1) & ~1;
+}
+template <typename T> int record_words(int dim) { return rec_words<T>(dim); }
+template int record_words<float>(int);
+template int record_words<double>(int);
+
+// movers leaving through the lower / upper face of `axis` go to the send buffers
+// (check_boundary + pack, os-spec-boundary.f03:538-623, os-spec-comm.f90:454-522).  The upper
+// message is re-indexed by the sender (ix - nx), the lower one by the receiver (ix + its nx).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    classify_kernel(MoverView<T> mv, int dim, int axis, int nx_axis, int send_lo, int send_up, uint32_t *buf_lo,
+                    uint32_t *buf_up, int *cnt2, int cap_rec, int *errflag) {
+  const int n = min(*mv.count, mv.cap);
+  const int rw = rec_words<T>(dim);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (mv.ix[0][i] == INT_MIN) continue;
+    const int v = mv.ix[axis][i];
+    int side = -1;
+    if (v < 1 && send_lo) side = 0;
+    else if (v > nx_axis && send_up) side = 1;
+    if (side < 0) continue;
+    const int k = atomicAdd(&cnt2[side], 1);
+    if (k >= cap_rec) { atomicOr(errflag, ERRF_SEND_OVERFLOW); continue; }
+    uint32_t *r = (side ? buf_up : buf_lo) + (size_t)k * rw;
+    const long long tag = mv.tag[i];
+    r[0] = (uint32_t)(tag & 0xffffffffll);
+    r[1] = (uint32_t)((unsigned long long)tag >> 32);
+    T *f = reinterpret_cast<T *>(r + 2);
+    for (int d = 0; d < dim; d++) f[d] = mv.x[d][i];
+    for (int d = 0; d < 3; d++) f[dim + d] = mv.p[d][i];
+    f[dim + 3] = mv.q[i];
+    int *ii = reinterpret_cast<int *>(f + dim + 4);
+    for (int d = 0; d < dim; d++) ii[d] = mv.ix[d][i] - ((side == 1 && d == axis) ? nx_axis : 0);
+    mv.ix[0][i] = INT_MIN;  // no longer ours
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    unpack_kernel(const uint32_t *buf, int nrec, int dim, int axis, int add_axis, MoverView<T> mv, int *errflag) {
+  const int rw = rec_words<T>(dim);
+  __shared__ int s_base;
+  // reserve a contiguous range per block
+  const int first = blockIdx.x * blockDim.x;
+  const int nb = min(blockDim.x, nrec - first);
+  if (nb <= 0) return;
+  if (threadIdx.x == 0) {
+    int b = atomicAdd(mv.count, nb);
+    if (b + nb > mv.cap) { atomicOr(errflag, ERRF_MOVER_OVERFLOW); b = -1; }
+    s_base = b;
+  }
+  __syncthreads();
+  if (s_base < 0 || (int)threadIdx.x >= nb) return;
+  const int i = first + threadIdx.x, k = s_base + threadIdx.x;
+  const uint32_t *r = buf + (size_t)i * rw;
+  mv.tag[k] = (long long)(((unsigned long long)r[1] << 32) | r[0]);
+  const T *f = reinterpret_cast<const T *>(r + 2);
+  for (int d = 0; d < dim; d++) mv.x[d][k] = f[d];
+  for (int d = 0; d < 3; d++) mv.p[d][k] = f[dim + d];
+  mv.q[k] = f[dim + 3];
+  const int *ii = reinterpret_cast<const int *>(f + dim + 4);
+  for (int d = 0; d < dim; d++) mv.ix[d][k] = ii[d] + ((d == axis) ? add_axis : 0);
+}
+
+// ---- host-side launchers ---------------------------------------------------------------------
+#define LAUNCHED(n)            \
+  *launches += (n);            \
+  OSGPU_CUDA(cudaGetLastError()); \
+  return OSGPU_OK
+
+static int blocks_for(long long n) {
+  long long b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > GRID_STRIDE_BLOCKS * 4) b = GRID_STRIDE_BLOCKS * 4;
+  return (int)b;
+}
+
+template <typename T>
+int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *tile_cnt,
+              int *errflag, cudaStream_t st, long long *launches) {
+  if (np == 0) return OSGPU_OK;
+  count_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, g.dim, tl, g, tile_cnt, errflag);
+  LAUNCHED(1);
+}
+template <typename T>
+int bin_scatter(const AosParticles<T> &in, long long np, long long tag_base, const Grid &g, const Tiling &tl,
+                const int *tile_off, int *cursor, const SpeciesView<T> &sp, cudaStream_t st,
+                long long *launches) {
+  if (np == 0) return OSGPU_OK;
+  scatter_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, tag_base, g.dim, tl, g, tile_off, cursor, sp);
+  LAUNCHED(1);
+}
+template <typename T>
+int gather_download(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const long long *out_off,
+                    const Grid &g, const Tiling &tl, int *oix, T *ox, T *op, T *oq, long long *otag, int by_tag,
+                    cudaStream_t st, long long *launches) {
+  gather_kernel<T><<<tl.ntile, 256, 0, st>>>(sp, tile_off, tile_cnt, out_off, g.dim, tl, oix, ox, op, oq, otag,
+                                             by_tag);
+  LAUNCHED(1);
+}
+template <typename T>
+int movers_download(const MoverView<T> &mv, long long out_base, const Grid &g, int *oix, T *ox, T *op, T *oq,
+                    long long *otag, int by_tag, cudaStream_t st, long long *launches) {
+  mover_gather_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, out_base, g.dim, oix, ox, op, oq, otag, by_tag);
+  LAUNCHED(1);
+}
+template <typename T>
+int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *wrap, const int *tile_off,
+                 const int *tile_cnt, int *tile_arr, int *errflag, cudaStream_t st, long long *launches) {
+  OSGPU_CUDA(cudaMemsetAsync(tile_arr, 0, sizeof(int) * tl.ntile, st));
+  route_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, tl, g, wrap[0], wrap[1], wrap[2], tile_arr, errflag);
+  capacity_kernel<<<(tl.ntile + 255) / 256, 256, 0, st>>>(tile_off, tile_cnt, tile_arr, tl.ntile, errflag);
+  LAUNCHED(2);
+}
+template <typename T>
+int movers_insert(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *tile_off, int *tile_cnt,
+                  const SpeciesView<T> &sp, cudaStream_t st, long long *launches) {
+  insert_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, tl, g, tile_off, tile_cnt, sp);
+  LAUNCHED(1);
+}
+template <typename T>
+int relayout(const SpeciesView<T> &src, const int *old_off, const int *tile_cnt, const SpeciesView<T> &dst,
+             const int *new_off, const Grid &g, const Tiling &tl, cudaStream_t st, long long *launches) {
+  relayout_kernel<T><<<tl.ntile, 256, 0, st>>>(src, old_off, tile_cnt, dst, new_off, g.dim);
+  LAUNCHED(1);
+}
+template <typename T>
+int movers_classify(const MoverView<T> &mv, const Grid &g, int axis, int send_lo, int send_up, uint32_t *buf_lo,
+                    uint32_t *buf_up, int *cnt2, int cap_rec, int *errflag, cudaStream_t st,
+                    long long *launches) {
+  classify_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, axis, g.nx[axis], send_lo, send_up, buf_lo,
+                                                         buf_up, cnt2, cap_rec, errflag);
+  LAUNCHED(1);
+}
+template <typename T>
+int movers_unpack(const uint32_t *buf, int nrec, const Grid &g, int axis, int add_axis, const MoverView<T> &mv,
+                  int *errflag, cudaStream_t st, long long *launches) {
+  if (nrec <= 0) return OSGPU_OK;
+  unpack_kernel<T><<<(nrec + 255) / 256, 256, 0, st>>>(buf, nrec, g.dim, axis, add_axis, mv, errflag);
+  LAUNCHED(1);
+}
+
+#define INST(T)                                                                                               \
+  template int bin_count<T>(const AosParticles<T> &, long long, const Grid &, const Tiling &, int *, int *,    \
+                            cudaStream_t, long long *);                                                       \
+  template int bin_scatter<T>(const AosParticles<T> &, long long, long long, const Grid &, const Tiling &,     \
+                              const int *, int *, const SpeciesView<T> &, cudaStream_t, long long *);          \
+  template int gather_download<T>(const SpeciesView<T> &, const int *, const int *, const long long *,         \
+                                  const Grid &, const Tiling &, int *, T *, T *, T *, long long *, int,        \
+                                  cudaStream_t, long long *);                                                 \
+  template int movers_download<T>(const MoverView<T> &, long long, const Grid &, int *, T *, T *, T *,         \
+                                  long long *, int, cudaStream_t, long long *);                               \
+  template int movers_route<T>(const MoverView<T> &, const Grid &, const Tiling &, const int *, const int *,   \
+                               const int *, int *, int *, cudaStream_t, long long *);                         \
+  template int movers_insert<T>(const MoverView<T> &, const Grid &, const Tiling &, const int *, int *,        \
+                                const SpeciesView<T> &, cudaStream_t, long long *);                           \
+  template int relayout<T>(const SpeciesView<T> &, const int *, const int *, const SpeciesView<T> &,           \
+                           const int *, const Grid &, const Tiling &, cudaStream_t, long long *);             \
+  template int movers_classify<T>(const MoverView<T> &, const Grid &, int, int, int, uint32_t *, uint32_t *,   \
+                                  int *, int, int *, cudaStream_t, long long *);                              \
+  template int movers_unpack<T>(const uint32_t *, int, const Grid &, int, int, const MoverView<T> &, int *,    \
+                                cudaStream_t, long long *);
+INST(float)
+INST(double)
+
+}  // namespace osgpu

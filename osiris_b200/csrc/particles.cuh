@@ -1,0 +1,48 @@
+// particles.cuh -- launch interface of the particle bookkeeping kernels (particles.cu)
+#pragma once
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace osgpu {
+
+// host-layout (Fortran) particle arrays staged on the device: x(D,np), ix(D,np), p(3,np), q(np)
+template <typename T> struct AosParticles {
+  const int *ix;
+  const T *x;
+  const T *p;
+  const T *q;
+  const long long *tag;  // may be null
+};
+
+template <typename T>
+int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *tile_cnt,
+              int *errflag, cudaStream_t st, long long *launches);
+template <typename T>
+int bin_scatter(const AosParticles<T> &in, long long np, long long tag_base, const Grid &g, const Tiling &tl,
+                const int *tile_off, int *cursor, const SpeciesView<T> &sp, cudaStream_t st, long long *launches);
+template <typename T>
+int gather_download(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const long long *out_off,
+                    const Grid &g, const Tiling &tl, int *oix, T *ox, T *op, T *oq, long long *otag, int by_tag,
+                    cudaStream_t st, long long *launches);
+template <typename T>
+int movers_download(const MoverView<T> &mv, long long out_base, const Grid &g, int *oix, T *ox, T *op, T *oq,
+                    long long *otag, int by_tag, cudaStream_t st, long long *launches);
+template <typename T>
+int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *wrap, const int *tile_off,
+                 const int *tile_cnt, int *tile_arr, int *errflag, cudaStream_t st, long long *launches);
+template <typename T>
+int movers_insert(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *tile_off, int *tile_cnt,
+                  const SpeciesView<T> &sp, cudaStream_t st, long long *launches);
+template <typename T>
+int relayout(const SpeciesView<T> &src, const int *old_off, const int *tile_cnt, const SpeciesView<T> &dst,
+             const int *new_off, const Grid &g, const Tiling &tl, cudaStream_t st, long long *launches);
+template <typename T> int record_words(int dim);
+template <typename T>
+int movers_classify(const MoverView<T> &mv, const Grid &g, int axis, int send_lo, int send_up, uint32_t *buf_lo,
+                    uint32_t *buf_up, int *cnt2, int cap_rec, int *errflag, cudaStream_t st, long long *launches);
+template <typename T>
+int movers_unpack(const uint32_t *buf, int nrec, const Grid &g, int axis, int add_axis, const MoverView<T> &mv,
+                  int *errflag, cudaStream_t st, long long *launches);
+
+}  // namespace osgpu

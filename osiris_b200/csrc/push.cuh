@@ -1,0 +1,33 @@
+// push.cuh -- launch interface of the fused push + deposit kernel (push.cu)
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace osgpu {
+
+// tensor maps of E1..3, B1..3 (one box = one tile + halo), passed as a __grid_constant__
+struct alignas(64) TmaMaps {
+  CUtensorMap m[6];
+};
+
+template <typename T> struct PushArgs {
+  SpeciesView<T> sp;
+  MoverView<T> mv;
+  const int *tile_off;
+  int *tile_cnt;
+  T *J[3];
+  Grid g;
+  Tiling tl;
+  pic::PushConst<T> k;
+  double *ene;   // += sum(q * u^2/(gamma+1)) over the species
+  int *errflag;
+};
+
+template <typename T>
+int launch_push_deposit(int dim, int order, const TmaMaps &maps, const PushArgs<T> &a, int ntile,
+                        cudaStream_t st);
+// TMA box (elements, fastest first) and dynamic shared memory of the kernel for (dim, order)
+template <typename T> void push_tile_shape(int dim, int order, int *box, int *smem_bytes);
+
+}  // namespace osgpu

@@ -1,0 +1,269 @@
+"""Host-side mirror of the OSIRIS objects that bound the hot path, driving the C ABI.
+
+Names follow the reference so the parity tests read like its time step
+(source/os-simulation.f03:498-666):
+
+    sim.emf.update_boundary(); sim.part.advance_deposit(); sim.part.update_boundary();
+    sim.jay.update_boundary(); sim.emf.advance()            # == sim.iter()
+
+and the device-residency hooks keep their name (`fill_data`, spec/os-species.f03:1867-1894,
+emf/os-emf.f03:1158-1184, current/os-current-define.f03:734-757).  Host arrays use the Fortran
+layouts: particles x(D,np) -> numpy (np, D); grids f(3,S1,S2,S3) -> numpy (S3, S2, S1, 3).
+All compute goes through libosiris_b200.so; nothing here touches particle or grid values.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import Config, check, ptr
+
+
+def min_gc(order, smooth_order=0, moving=()):
+    """Guard cells (lower[D]-like scalar pair) the reference would allocate for E/B and J:
+    particles need (order, order+1) (particles/os-particles.f03:329-346), Yee (1,2)
+    (emf/solver/os-emf-solver-yee.f03:458-468), + smoothing order on both sides
+    (emf/os-emf.f03:663-724, current/os-current-define.f03:192-205)."""
+    out = (C.c_int32 * 2)()
+    check(_lib.load().osgpu_min_gc(order, out))
+    return int(out[0]) + smooth_order, int(out[1]) + smooth_order
+
+
+class NodeConf:
+    """t_node_conf (source/os-nconf.f03:45-107): cartesian rank layout, x fastest."""
+
+    def __init__(self, dim, node_number=None, if_periodic=None, rank=0):
+        self.dim = dim
+        self.node_number = list(node_number) if node_number is not None else [1] * dim
+        self.if_periodic = [bool(p) for p in (if_periodic if if_periodic is not None else [True] * dim)]
+        self.rank = rank
+        self.nranks = int(np.prod(self.node_number))
+        L = _lib.load()
+        dims = (C.c_int32 * 3)(*(self.node_number + [1] * (3 - dim)))
+        co = (C.c_int32 * 3)()
+        L.osgpu_cart_coords(dim, dims, rank, co)
+        self.coords = [int(co[d]) for d in range(dim)]
+        nb = (C.c_int32 * 6)()
+        per = (C.c_int32 * 3)(*([int(p) for p in self.if_periodic] + [0] * (3 - dim)))
+        L.osgpu_cart_neighbors(dim, dims, per, rank, nb)
+        # neighbor(2, D): [d][0] lower, [d][1] upper
+        self.neighbor = [[int(nb[2 * d]), int(nb[2 * d + 1])] for d in range(dim)]
+
+
+class Species:
+    """t_species (spec/os-spec-define.f03:327-549) device mirror."""
+
+    def __init__(self, sim, sp_id, name, rqm, num_par_max):
+        self.sim, self.sp_id, self.name, self.rqm = sim, sp_id, name, float(rqm)
+        check(sim._L.osgpu_species_create(sim._h, sp_id, float(rqm), int(num_par_max)))
+
+    def upload(self, ix, x, p, q, tag=None):
+        dt = self.sim.dtype
+        ix = np.ascontiguousarray(ix, np.int32)
+        x, p, q = (np.ascontiguousarray(a, dt) for a in (x, p, q))
+        tag = None if tag is None else np.ascontiguousarray(tag, np.int64)
+        check(self.sim._L.osgpu_species_upload(self.sim._h, self.sp_id, q.shape[0], ptr(ix), ptr(x), ptr(p),
+                                               ptr(q), ptr(tag)))
+
+    @property
+    def num_par(self):
+        n = self.sim._L.osgpu_species_count(self.sim._h, self.sp_id)
+        if n < 0:
+            raise _lib.OsgpuError(-1, "species_count failed")
+        return int(n)
+
+    def fill_data(self, sort_by_tag=True):
+        """Device -> host copy of the particle buffers: returns dict(ix, x, p, q, tag)."""
+        n, D, dt = self.num_par, self.sim.dim, self.sim.dtype
+        out = dict(ix=np.zeros((n, D), np.int32), x=np.zeros((n, D), dt), p=np.zeros((n, 3), dt),
+                   q=np.zeros(n, dt), tag=np.zeros(n, np.int64))
+        check(self.sim._L.osgpu_species_download(self.sim._h, self.sp_id, ptr(out["ix"]), ptr(out["x"]),
+                                                 ptr(out["p"]), ptr(out["q"]), ptr(out["tag"])))
+        if sort_by_tag:
+            o = np.argsort(out["tag"], kind="stable")
+            out = {k: v[o] for k, v in out.items()}
+        return out
+
+
+class _Emf:
+    """t_emf (emf/os-emf-define.f03:197-281)"""
+
+    def __init__(self, sim):
+        self.sim = sim
+
+    def upload(self, e, b):
+        dt = self.sim.dtype
+        e, b = np.ascontiguousarray(e, dt), np.ascontiguousarray(b, dt)
+        assert e.shape == self.sim.emf_shape and b.shape == self.sim.emf_shape, (e.shape, self.sim.emf_shape)
+        check(self.sim._L.osgpu_fields_upload(self.sim._h, ptr(e), ptr(b)))
+
+    def fill_data(self):
+        e = np.zeros(self.sim.emf_shape, self.sim.dtype)
+        b = np.zeros(self.sim.emf_shape, self.sim.dtype)
+        check(self.sim._L.osgpu_fields_download(self.sim._h, ptr(e), ptr(b)))
+        return e, b
+
+    def update_boundary(self):
+        check(self.sim._L.osgpu_emf_update_boundary(self.sim._h))
+
+    def advance(self):
+        check(self.sim._L.osgpu_emf_advance(self.sim._h))
+
+    def energy(self):
+        out = np.zeros(6, np.float64)
+        check(self.sim._L.osgpu_field_energy(self.sim._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+
+class _Current:
+    """t_current (current/os-current-define.f03:42-95); pf(1) only: one J grid per GPU"""
+
+    def __init__(self, sim):
+        self.sim = sim
+
+    def upload(self, j):
+        j = np.ascontiguousarray(j, self.sim.dtype)
+        assert j.shape == self.sim.jay_shape
+        check(self.sim._L.osgpu_current_upload(self.sim._h, ptr(j)))
+
+    def fill_data(self):
+        j = np.zeros(self.sim.jay_shape, self.sim.dtype)
+        check(self.sim._L.osgpu_current_download(self.sim._h, ptr(j)))
+        return j
+
+    def update_boundary(self):
+        check(self.sim._L.osgpu_current_update_boundary(self.sim._h))
+
+
+class _Particles:
+    """t_particles (particles/os-particles.f03): the container of all species"""
+
+    def __init__(self, sim):
+        self.sim = sim
+        self.species = []
+
+    def advance_deposit(self):
+        """Returns the time-centred kinetic energy sum(q u^2/(gamma+1)) per species."""
+        ene = np.zeros(max(1, len(self.species)), np.float64)
+        check(self.sim._L.osgpu_advance_deposit(self.sim._h, ene.ctypes.data_as(C.POINTER(C.c_double))))
+        return ene
+
+    def update_boundary(self):
+        check(self.sim._L.osgpu_particles_update_boundary(self.sim._h))
+
+    def sort(self):
+        check(self.sim._L.osgpu_sort(self.sim._h))
+
+
+class Simulation:
+    """The hot part of t_simulation (os-simulation.f03).  One instance per rank / GPU."""
+
+    def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
+                 node_conf=None, nccl_id=None, device=-1, smooth_order=0):
+        self._L = _lib.load()
+        self.dim, self.order = int(dim), int(interpolation)
+        self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
+        self.nx = [int(v) for v in nx]
+        self.dx = [float(v) for v in dx]
+        self.dt = float(dt)
+        lo, up = min_gc(self.order, smooth_order)
+        self.gc_emf = gc_emf if gc_emf is not None else ([lo] * dim, [up] * dim)
+        self.gc_jay = gc_jay if gc_jay is not None else ([lo] * dim, [up] * dim)
+        self.no_co = node_conf if node_conf is not None else NodeConf(dim)
+        cfg = Config()
+        cfg.dim, cfg.order, cfg.real_bytes, cfg.nspecies = self.dim, self.order, np.dtype(self.dtype).itemsize, nspecies
+        for d in range(dim):
+            cfg.nx[d] = self.nx[d]
+            cfg.dx[d] = self.dx[d]
+            for s in range(2):
+                cfg.gc_emf[s][d] = int(self.gc_emf[s][d])
+                cfg.gc_jay[s][d] = int(self.gc_jay[s][d])
+            cfg.node_dims[d] = self.no_co.node_number[d]
+            cfg.node_coords[d] = self.no_co.coords[d]
+            cfg.periodic[d] = int(self.no_co.if_periodic[d])
+        cfg.dt = self.dt
+        cfg.rank, cfg.nranks, cfg.device, cfg.smooth_order = self.no_co.rank, self.no_co.nranks, device, smooth_order
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        idbuf = None
+        if nccl_id is not None:
+            idbuf = (C.c_char * _lib.NCCL_ID_BYTES).from_buffer_copy(bytes(nccl_id))
+        check(self._L.osgpu_init(C.byref(self._h), C.byref(cfg), idbuf))
+        self.emf, self.jay, self.part = _Emf(self), _Current(self), _Particles(self)
+        self.nspecies = nspecies
+
+    # padded host array shapes (numpy order: slowest first, component last)
+    def _shape(self, gc):
+        return tuple(self.nx[d] + gc[0][d] + gc[1][d] for d in reversed(range(self.dim))) + (3,)
+
+    @property
+    def emf_shape(self):
+        return self._shape(self.gc_emf)
+
+    @property
+    def jay_shape(self):
+        return self._shape(self.gc_jay)
+
+    def add_species(self, name, rqm, num_par_max):
+        sp = Species(self, len(self.part.species), name, rqm, num_par_max)
+        self.part.species.append(sp)
+        return sp
+
+    def iter(self, nsteps=1):
+        """nsteps time steps entirely on the GPU; returns per-species kinetic energy sums of the
+        last step (iter_sim, os-simulation.f03:561-661)."""
+        ene = np.zeros(max(1, self.nspecies), np.float64)
+        check(self._L.osgpu_step(self._h, int(nsteps), ene.ctypes.data_as(C.POINTER(C.c_double))))
+        return ene
+
+    def phase_times_ms(self):
+        out = np.zeros(6, np.float64)
+        check(self._L.osgpu_phase_times_ms(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return dict(zip(("update emf boundary", "advance deposit", "update particle boundary",
+                         "update current boundary", "field solver", "loop"), out))
+
+    @property
+    def launch_count(self):
+        return int(self._L.osgpu_launch_count(self._h))
+
+    @property
+    def stream(self):
+        return self._L.osgpu_stream(self._h)
+
+    def sync(self):
+        check(self._L.osgpu_sync(self._h))
+
+    def close(self):
+        if self._h:
+            self._L.osgpu_finalize(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id():
+    buf = (C.c_char * _lib.NCCL_ID_BYTES)()
+    check(_lib.load().osgpu_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def vadvance_deposit(dim, order, ix, x, u, q, rqm, e, b, emf_gc, j, j_gc, dx, dt, i0=1, i1=None):
+    """The stateless pusher with the reference's C signature (host arrays in and out, J and the
+    energy accumulated): osgpu_vadvance_deposit_{2d,3d}_s{order}[_d].  Returns the energy added."""
+    L = _lib.load()
+    dtp = x.dtype
+    n = q.shape[0] if i1 is None else i1
+    esz = np.ascontiguousarray(e.shape[::-1][1:1 + dim], np.int32)
+    jsz = np.ascontiguousarray(j.shape[::-1][1:1 + dim], np.int32)
+    eoff = np.ascontiguousarray(emf_gc[0], np.int32)
+    joff = np.ascontiguousarray(j_gc[0], np.int32)
+    dxa = np.ascontiguousarray(dx, np.float64)
+    ene = C.c_double(0.0)
+    check(L.osgpu_vadvance_deposit(dim, order, dtp.itemsize, ptr(ix), ptr(x), ptr(u), ptr(q), i0, n, float(rqm),
+                                   ptr(e), ptr(b), ptr(esz), ptr(eoff), ptr(j), ptr(jsz), ptr(joff), ptr(dxa),
+                                   float(dt), C.byref(ene)))
+    return ene.value

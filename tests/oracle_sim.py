@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE: the reference time step composed from the oracle's pieces, with the same
+method names as osiris_b200.simulation.Simulation so a test can drive both side by side.
+Single rank, periodic (the reference's update_periodic_vdf / periodic particle wrap)."""
+import numpy as np
+
+from oracle.bindings import Oracle, aligned
+
+
+class OracleSim:
+    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None):
+        self.orc = Oracle(precision)
+        self.dtype = self.orc.dtype
+        self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
+        lo, up = max(order, 1), max(order + 1, 2)
+        self.gc_emf = gc_emf if gc_emf is not None else ([lo] * dim, [up] * dim)
+        self.gc_jay = gc_jay if gc_jay is not None else ([lo] * dim, [up] * dim)
+        sh = lambda gc: tuple(self.nx[d] + gc[0][d] + gc[1][d] for d in reversed(range(dim))) + (3,)
+        self.e = np.zeros(sh(self.gc_emf), self.dtype)
+        self.b = np.zeros(sh(self.gc_emf), self.dtype)
+        self.j = np.zeros(sh(self.gc_jay), self.dtype)
+        self.species = []
+        # particles use dt rounded to their precision (spec/os-spec-vpush.f03:374)
+        self.dtp = float(self.dtype(self.dt))
+
+    def add_species(self, rqm, ix, x, p, q):
+        sp = dict(rqm=float(rqm), ix=np.ascontiguousarray(ix, np.int32).copy(),
+                  x=np.ascontiguousarray(x, self.dtype).copy(), p=np.ascontiguousarray(p, self.dtype).copy(),
+                  q=np.ascontiguousarray(q, self.dtype).copy())
+        self.species.append(sp)
+        return sp
+
+    def emf_update_boundary(self):
+        self.orc.update_periodic(self.dim, self.e, self.nx, self.gc_emf, "replace")
+        self.orc.update_periodic(self.dim, self.b, self.nx, self.gc_emf, "replace")
+
+    def advance_deposit(self):
+        self.j[...] = 0
+        ene = []
+        for sp in self.species:
+            if sp["q"].shape[0] == 0:
+                ene.append(0.0)
+                continue
+            ene.append(self.orc.advance_deposit(self.dim, self.order, sp["ix"], sp["x"], sp["p"], sp["q"],
+                                                sp["rqm"], self.e, self.b, self.gc_emf, self.j, self.gc_jay,
+                                                self.dx, self.dtp))
+        return np.array(ene)
+
+    def particles_update_boundary(self):
+        for sp in self.species:
+            self.orc.particles_periodic(self.dim, sp["ix"], self.nx)
+
+    def current_update_boundary(self):
+        self.orc.update_periodic(self.dim, self.j, self.nx, self.gc_jay, "add")
+
+    def emf_advance(self):
+        assert self.gc_emf == self.gc_jay
+        self.orc.yee_advance(self.dim, self.e, self.b, self.j, self.nx, self.gc_emf, self.dx, self.dt)
+
+    def iter(self, nsteps=1):
+        ene = None
+        for _ in range(nsteps):
+            self.emf_update_boundary()
+            ene = self.advance_deposit()
+            self.particles_update_boundary()
+            self.current_update_boundary()
+            self.emf_advance()
+        return ene
+
+    def field_energy(self):
+        return np.concatenate([self.orc.field_energy(self.dim, f, self.nx, self.gc_emf, self.dx)
+                               for f in (self.e, self.b)])
+
+
+def random_case(dim, order, prec, nx, ppc, seed=0, umax=0.6, gc=None, efield=0.5):
+    """random particles + random fields in the reference layouts"""
+    dt_ = np.float32 if prec == "f32" else np.float64
+    rng = np.random.default_rng(seed)
+    lo, up = max(order, 1), max(order + 1, 2)
+    gc = gc if gc is not None else ([lo] * dim, [up] * dim)
+    shape = tuple(nx[d] + gc[0][d] + gc[1][d] for d in reversed(range(dim))) + (3,)
+    e = (rng.standard_normal(shape) * efield).astype(dt_)
+    b = (rng.standard_normal(shape) * efield).astype(dt_)
+    n = int(np.prod(nx)) * ppc
+    ix = np.stack([rng.integers(1, nx[d] + 1, n) for d in range(dim)], -1).astype(np.int32)
+    x = (rng.random((n, dim)) - 0.5).astype(dt_)
+    x[x >= 0.5] = dt_(0.49)
+    u = ((rng.random((n, 3)) * 2 - 1) * umax * 3).astype(dt_)
+    q = (-(rng.random(n) + 0.5) / ppc).astype(dt_)
+    return dict(nx=list(nx), gc=gc, e=e, b=b, ix=ix, x=x, u=u, q=q)

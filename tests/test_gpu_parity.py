@@ -1,0 +1,262 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (the reference's own ISA variants differ by 1 ulp per particle and
+~3e-7 in J): ix exact; x and p bit-identical (same FMA statement as the reference's AVX2 kernels);
+J max|dJ| <= 1e-5 max|J| in fp32, 1e-12 in fp64 (summation order differs: shared-memory atomics);
+energy 1e-6 / 1e-12 relative; Yee E/B bit-identical given the same J.
+"""
+import numpy as np
+import pytest
+
+from oracle_sim import OracleSim, random_case
+
+pytestmark = pytest.mark.gpu
+
+JTOL = {"f32": 1e-5, "f64": 1e-12}
+ETOL = {"f32": 1e-6, "f64": 1e-12}
+SHAPES = {2: [37, 21], 3: [19, 13, 11]}
+DX = {2: [0.1, 0.12], 3: [0.1, 0.12, 0.09]}
+
+
+def _close_j(j, jr, prec):
+    scale = np.abs(jr).max()
+    assert np.abs(j - jr).max() <= JTOL[prec] * scale, (np.abs(j - jr).max() / scale)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_vadvance_deposit_matches_oracle(built, dim, order, prec):
+    """the stateless entry point with the reference C signature, host arrays in and out"""
+    from osiris_b200.simulation import vadvance_deposit
+    from oracle.bindings import Oracle
+    c = random_case(dim, order, prec, SHAPES[dim], ppc=6, seed=10 * dim + order)
+    orc = Oracle(prec)
+    dt = 0.05
+    dtp = float(c["x"].dtype.type(dt))
+    j0 = (np.random.default_rng(1).standard_normal(c["e"].shape) * 0.01).astype(c["x"].dtype)
+    # oracle
+    ixr, xr, ur, jr = c["ix"].copy(), c["x"].copy(), c["u"].copy(), j0.copy()
+    ene_r = orc.advance_deposit(dim, order, ixr, xr, ur, c["q"], -1.0, c["e"], c["b"], c["gc"], jr, c["gc"],
+                                DX[dim], dtp)
+    # GPU
+    ix, x, u, j = c["ix"].copy(), c["x"].copy(), c["u"].copy(), j0.copy()
+    ene = vadvance_deposit(dim, order, ix, x, u, c["q"], -1.0, c["e"], c["b"], c["gc"], j, c["gc"], DX[dim], dtp)
+    assert np.array_equal(ix, ixr)
+    assert np.array_equal(x, xr), np.abs(x - xr).max()
+    assert np.array_equal(u, ur), np.abs(u - ur).max()
+    _close_j(j, jr, prec)
+    assert abs(ene - ene_r) <= ETOL[prec] * abs(ene_r)
+
+
+def test_vadvance_deposit_subrange(built):
+    """i0..i1 selects a 1-based inclusive sub-range; everything else is untouched"""
+    from osiris_b200.simulation import vadvance_deposit
+    from oracle.bindings import Oracle
+    dim, order, prec = 2, 2, "f32"
+    c = random_case(dim, order, prec, SHAPES[dim], ppc=3, seed=5)
+    orc = Oracle(prec)
+    n = c["q"].shape[0]
+    i0, i1 = 101, n - 57
+    dtp = float(np.float32(0.05))
+    ixr, xr, ur, jr = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+    orc.advance_deposit(dim, order, ixr, xr, ur, c["q"], -1.0, c["e"], c["b"], c["gc"], jr, c["gc"], DX[dim], dtp,
+                        i0=i0, i1=i1)
+    ix, x, u, j = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+    vadvance_deposit(dim, order, ix, x, u, c["q"], -1.0, c["e"], c["b"], c["gc"], j, c["gc"], DX[dim], dtp,
+                     i0=i0, i1=i1)
+    assert np.array_equal(ix, ixr) and np.array_equal(x, xr) and np.array_equal(u, ur)
+    assert np.array_equal(x[:i0 - 1], c["x"][:i0 - 1]) and np.array_equal(x[i1:], c["x"][i1:])
+    _close_j(j, jr, prec)
+
+
+def _pair(dim, order, prec, nx, ppc, seed=0, dt=None, nspecies=1, umax=0.3):
+    from osiris_b200.simulation import Simulation
+    dx = DX[dim]
+    dt = dt if dt is not None else 0.4 * min(dx) / np.sqrt(dim)
+    c = random_case(dim, order, prec, nx, ppc, seed=seed, umax=umax, efield=0.05)
+    sim = Simulation(dim, order, nx, dx, dt, precision=prec, nspecies=nspecies, gc_emf=c["gc"], gc_jay=c["gc"])
+    ora = OracleSim(dim, order, nx, dx, dt, precision=prec, gc_emf=c["gc"], gc_jay=c["gc"])
+    ora.e[...] = c["e"]
+    ora.b[...] = c["b"]
+    sim.emf.upload(c["e"], c["b"])
+    n = c["q"].shape[0]
+    per = n // nspecies
+    for s in range(nspecies):
+        sl = slice(s * per, (s + 1) * per)
+        rqm = -1.0 if s == 0 else 2.0
+        sp = sim.add_species(f"sp{s}", rqm, per + per // 2 + 1024)
+        sp.upload(c["ix"][sl], c["x"][sl], c["u"][sl], c["q"][sl])
+        ora.add_species(rqm, c["ix"][sl], c["x"][sl], c["u"][sl], c["q"][sl])
+    return sim, ora
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("dim,order", [(2, 1), (2, 2), (3, 2), (3, 3), (2, 4), (3, 1)])
+def test_step_phases_match_oracle(built, dim, order, prec):
+    """every phase of iter_sim, one at a time, state compared after each"""
+    sim, ora = _pair(dim, order, prec, SHAPES[dim], ppc=5, seed=3, nspecies=2)
+    # E/B guard cells: copies -> exact
+    sim.emf.update_boundary()
+    ora.emf_update_boundary()
+    e, b = sim.emf.fill_data()
+    assert np.array_equal(e, ora.e) and np.array_equal(b, ora.b)
+    # push + deposit
+    ene = sim.part.advance_deposit()
+    ene_r = ora.advance_deposit()
+    assert np.allclose(ene, ene_r, rtol=ETOL[prec], atol=0)
+    j = sim.jay.fill_data()
+    _close_j(j, ora.j, prec)
+    # particle boundary: periodic wrap + re-binning
+    sim.part.update_boundary()
+    ora.particles_update_boundary()
+    for sp, spr in zip(sim.part.species, ora.species):
+        d = sp.fill_data()
+        assert d["q"].shape[0] == spr["q"].shape[0]
+        assert np.array_equal(d["tag"], np.arange(spr["q"].shape[0]))
+        assert np.array_equal(d["ix"], spr["ix"])
+        assert np.array_equal(d["x"], spr["x"]) and np.array_equal(d["p"], spr["p"])
+        assert np.array_equal(d["q"], spr["q"])
+    # J guard cells: sums of the two images
+    sim.jay.update_boundary()
+    ora.current_update_boundary()
+    j = sim.jay.fill_data()
+    _close_j(j, ora.j, prec)
+    # Yee with identical J: bit-exact
+    sim.jay.upload(ora.j)
+    sim.emf.advance()
+    ora.emf_advance()
+    e, b = sim.emf.fill_data()
+    assert np.array_equal(e, ora.e), np.abs(e - ora.e).max()
+    assert np.array_equal(b, ora.b), np.abs(b - ora.b).max()
+    assert np.allclose(sim.emf.energy(), ora.field_energy(), rtol=1e-12)
+    sim.close()
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("dim,order", [(2, 2), (3, 2), (3, 1)])
+def test_n_steps_match_oracle(built, dim, order, prec):
+    """N full steps on the device (one osgpu_step call) against N oracle steps"""
+    nsteps = 8
+    sim, ora = _pair(dim, order, prec, SHAPES[dim], ppc=4, seed=7, nspecies=1, umax=0.1)
+    ene = sim.iter(nsteps)
+    ene_r = ora.iter(nsteps)
+    tol = 2e-4 if prec == "f32" else 1e-9
+    assert np.allclose(ene, ene_r, rtol=tol)
+    assert np.allclose(sim.emf.energy(), ora.field_energy(), rtol=tol)
+    d = sim.part.species[0].fill_data()
+    r = ora.species[0]
+    assert d["q"].shape[0] == r["q"].shape[0]
+    # positions as cell + offset (a particle within rounding of a cell face may sit on either side)
+    pos = d["ix"] + d["x"].astype(np.float64)
+    pos_r = r["ix"] + r["x"].astype(np.float64)
+    nxa = np.array(SHAPES[dim], np.float64)
+    dd = np.abs(pos - pos_r)
+    dd = np.minimum(dd, nxa - dd)
+    assert dd.max() < (1e-3 if prec == "f32" else 1e-9), dd.max()
+    assert np.abs(d["p"] - r["p"]).max() < (1e-3 if prec == "f32" else 1e-9)
+    e, b = sim.emf.fill_data()
+    sc = max(np.abs(ora.e).max(), np.abs(ora.b).max())
+    assert np.abs(e - ora.e).max() <= (1e-3 if prec == "f32" else 1e-9) * sc
+    sim.close()
+
+
+def test_empty_and_single_particle(built):
+    from osiris_b200.simulation import Simulation
+    dim, order, nx, dx = 2, 1, [16, 16], [0.1, 0.1]
+    sim = Simulation(dim, order, nx, dx, 0.05, nspecies=2)
+    sim.add_species("empty", -1.0, 1024)
+    one = sim.add_species("one", -1.0, 1024)
+    one.upload(np.array([[16, 1]], np.int32), np.array([[0.49, -0.5]], np.float32),
+               np.array([[5.0, -5.0, 0.0]], np.float32), np.array([-1.0], np.float32))
+    ora = OracleSim(dim, order, nx, dx, 0.05)
+    ora.add_species(-1.0, np.zeros((0, 2), np.int32), np.zeros((0, 2)), np.zeros((0, 3)), np.zeros(0))
+    ora.add_species(-1.0, np.array([[16, 1]], np.int32), np.array([[0.49, -0.5]]), np.array([[5.0, -5.0, 0.0]]),
+                    np.array([-1.0]))
+    sim.iter(3)
+    ora.iter(3)
+    assert sim.part.species[0].num_par == 0
+    d = sim.part.species[1].fill_data()
+    assert np.array_equal(d["ix"], ora.species[1]["ix"])
+    assert np.allclose(d["x"], ora.species[1]["x"], atol=1e-5)
+    e, b = sim.emf.fill_data()
+    assert np.allclose(e, ora.e, atol=1e-5 * max(1e-30, np.abs(ora.e).max()))
+    sim.close()
+
+
+def test_all_particles_in_one_cell_and_tile_overflow(built):
+    """worst-case shared-memory atomic contention, then a drift that overflows the neighbouring
+    tile's slack and forces the counting-sort re-layout"""
+    from osiris_b200.simulation import Simulation
+    dim, order, nx, dx, dt = 2, 2, [64, 32], [0.1, 0.1], 0.05
+    n = 20000
+    rng = np.random.default_rng(0)
+    ix = np.tile(np.array([[15, 9]], np.int32), (n, 1))
+    x = (rng.random((n, 2)) - 0.5).astype(np.float32)
+    p = np.zeros((n, 3), np.float32)
+    p[:, 0] = 8.0  # v ~ c along +x: half a cell per step, everybody crosses into the next tile
+    q = np.full(n, -1.0 / n, np.float32)
+    sim = Simulation(dim, order, nx, dx, dt)
+    sp = sim.add_species("beam", -1.0, 2 * n)
+    sp.upload(ix, x, p, q)
+    ora = OracleSim(dim, order, nx, dx, dt)
+    ora.add_species(-1.0, ix, x, p, q)
+    for _ in range(6):
+        sim.iter(1)
+        ora.iter(1)
+    d = sp.fill_data()
+    assert d["q"].shape[0] == n
+    assert np.array_equal(d["ix"], ora.species[0]["ix"])
+    assert np.abs(d["x"] - ora.species[0]["x"]).max() < 1e-4
+    j = sim.jay.fill_data()
+    _close_j(j, ora.j, "f32")
+    sim.close()
+
+
+def test_golden_fixtures(built):
+    """outputs of the reference's own compiled AVX2 kernels (tests/golden/make_golden.py)"""
+    import glob
+    import os
+    from osiris_b200.simulation import vadvance_deposit
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "vadv_*.npz")))
+    assert files, "golden fixtures missing"
+    for f in files:
+        g = np.load(f)
+        dim, order = int(g["dim"]), int(g["order"])
+        prec = "f32" if g["x"].dtype == np.float32 else "f64"
+        gc = (list(g["gcl"]), list(g["gcu"]))
+        ix, x, u, j = g["ix"].copy(), g["x"].copy(), g["u"].copy(), np.zeros_like(g["e"])
+        ene = vadvance_deposit(dim, order, ix, x, u, g["q"], float(g["rqm"]), g["e"], g["b"], gc, j, gc,
+                               list(g["dx"]), float(g["dt"]))
+        assert np.array_equal(ix, g["ix_out"]), f
+        assert np.array_equal(x, g["x_out"]) and np.array_equal(u, g["u_out"]), f
+        _close_j(j, g["j_out"], prec)
+        assert abs(ene - float(g["ene_out"])) <= 10 * ETOL[prec] * abs(float(g["ene_out"]))
+
+
+def test_continuity_at_scale(built):
+    """size-independent property on a workload-sized grid: the deposit is charge conserving,
+    (rho_new - rho_old)/dt + div J = 0 with rho from the same-order spline"""
+    from osiris_b200.simulation import Simulation
+    from osiris_b200.loads import lattice_species
+    from oracle.bindings import Oracle
+    dim, order, nx, dx, dt = 2, 2, [256, 256], [0.1, 0.1], 0.05
+    part = lattice_species(nx, [4, 4], np.float32, uth=(0.3, 0.3, 0.3))
+    sim = Simulation(dim, order, nx, dx, dt)
+    sp = sim.add_species("e", -1.0, part["q"].shape[0] * 2)
+    sp.upload(part["ix"], part["x"], part["p"], part["q"])
+    orc = Oracle("f32")
+    gc = sim.gc_jay
+    shape = sim.jay_shape[:-1]
+    rho0 = orc.deposit_rho(dim, order, part["ix"], part["x"], part["q"], shape, gc)
+    sim.part.advance_deposit()
+    j = sim.jay.fill_data().astype(np.float64)
+    d = sp.fill_data()
+    rho1 = orc.deposit_rho(dim, order, d["ix"], d["x"], d["q"], shape, gc)
+    dtp = float(np.float32(dt))
+    div = (j[:, :, 0] - np.roll(j[:, :, 0], 1, axis=1)) / dx[0] + (j[:, :, 1] - np.roll(j[:, :, 1], 1, axis=0)) / dx[1]
+    res = (rho1 - rho0) / dtp + div
+    inner = (slice(gc[0][1] + 1, -gc[1][1] - 1), slice(gc[0][0] + 1, -gc[1][0] - 1))
+    scale = np.abs(div[inner]).max()
+    assert np.abs(res[1:-1, 1:-1]).max() < 2e-4 * scale, np.abs(res[1:-1, 1:-1]).max() / scale
+    sim.close()

@@ -35,7 +35,8 @@ extern thread_local int g_last_status;
 struct Grid {
   int dim;
   int nx[3];
-  int gl[3], gu[3];
+  int gl[3], gu[3];  // storage guard cells (gl[0] is padded so tile rows start 16-byte aligned)
+  int ul[3], uu[3];  // guard cells that take part in boundary updates (the host arrays' widths)
   int S[3];       // padded extents (S[2] = 1 in 2D)
   int P0;         // row pitch in elements
   long long vol;  // elements per component = P0 * S[1] * S[2]

@@ -147,13 +147,13 @@ __global__ void __launch_bounds__(256)
 template <typename T>
 int periodic_update(const Grid &g, T *const *comps, int ncomp, int axis, int mode, cudaStream_t st,
                     long long *launches) {
-  if (g.nx[axis] < g.gl[axis] + g.gu[axis]) {
+  if (g.nx[axis] < g.ul[axis] + g.uu[axis]) {
     set_error("periodic guard update needs nx >= gc_lower + gc_upper on axis %d", axis);
     return OSGPU_ERR_INVALID;
   }
   // lower guards: cells 1-gl..0 -> padded 0..gl-1; upper guards: cells nx+1..nx+gu
-  const Slab lo = make_slab(g, axis, 0, g.gl[axis] - 1);
-  const Slab up = make_slab(g, axis, g.nx[axis] + g.gl[axis], g.S[axis] - 1);
+  const Slab lo = make_slab(g, axis, g.gl[axis] - g.ul[axis], g.gl[axis] - 1);
+  const Slab up = make_slab(g, axis, g.nx[axis] + g.gl[axis], g.nx[axis] + g.gl[axis] + g.uu[axis] - 1);
   long long stride = 1;
   if (axis == 1) stride = g.P0;
   if (axis == 2) stride = (long long)g.P0 * g.S[1];

@@ -138,6 +138,15 @@ template <typename T> struct Sim final : SimBase {
                   std::max(min_gc_lower(order), 1), std::max(min_gc_upper(order), 2), order);
         return OSGPU_ERR_INVALID;
       }
+      g.ul[d] = g.gl[d];
+      g.uu[d] = g.gu[d];
+      if (d == 0) {
+        // TMA box loads need the first point of every tile row (gl + LP - 1 + k*TX) on a 16-byte
+        // boundary of the row: pad the lower guard region of the storage
+        const int halo_lo = ((order == 1) ? 0 : (order == 4 ? -2 : -1)) - 1;
+        const int q = 16 / (int)sizeof(T);
+        while ((g.gl[0] + halo_lo) % q != 0) g.gl[0]++;
+      }
       g.S[d] = g.nx[d] + g.gl[d] + g.gu[d];
       tl.T[d] = pic::tile_edge(dim, d);
       tl.nt[d] = (g.nx[d] + tl.T[d] - 1) / tl.T[d];
@@ -180,7 +189,7 @@ template <typename T> struct Sim final : SimBase {
       // field exchange buffers: widest slab (gl+gu cells) x largest cross-section x 6 components
       size_t big = 0;
       for (int d = 0; d < dim; d++) {
-        size_t v = (size_t)(g.gl[d] + g.gu[d]);
+        size_t v = (size_t)(g.ul[d] + g.uu[d]);
         for (int o = 0; o < 3; o++)
           if (o != d) v *= g.S[o];
         big = std::max(big, v);
@@ -481,7 +490,7 @@ template <typename T> struct Sim final : SimBase {
       }
       if (lo < 0 && up < 0) continue;
       int r[8];
-      osgpu_exchange_ranges(g.nx[d], g.gl[d], g.gu[d], mode, r);
+      osgpu_exchange_ranges(g.nx[d], g.ul[d], g.uu[d], mode, r);
       auto pad = [&](int cell) { return cell - 1 + g.gl[d]; };
       const long long vs_lo = slab_volume(g, d, pad(r[0]), pad(r[1])) * nc;  // to the lower neighbour
       const long long vs_up = slab_volume(g, d, pad(r[2]), pad(r[3])) * nc;  // to the upper neighbour

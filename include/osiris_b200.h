@@ -129,11 +129,13 @@ int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-
 /* field energy per component, interior cells: out6 = {E1,E2,E3,B1,B2,B3}
  * (emf/diagnostics/os-emf-diagnostics.f03:43-58); summed over this rank only */
 int osgpu_field_energy(osgpu_sim *sim, double *out6);
-/* device-timed duration (ms) of each phase of the last osgpu_step call, summed over its steps:
- * {emf_bnd, push_deposit, part_bnd, jay_bnd, solver, total}; feeds the m_logprof events
+/* device-timed duration (ms, CUDA events on the handle's stream) of the last osgpu_step call,
+ * summed over its steps: out8 = {emf_bnd, push_deposit, part_bnd, jay_bnd, solver, whole call
+ * (first launch to last completion, gaps included), push kernel alone (single species), 0};
+ * feeds the m_logprof events
  * 'update emf boundary', 'advance deposit', 'update particle boundary', 'update current
  * boundary', 'field solver' (os-logprof.f90:146-260). */
-int osgpu_phase_times_ms(osgpu_sim *sim, double *out6);
+int osgpu_phase_times_ms(osgpu_sim *sim, double *out8);
 /* number of kernel launches issued by this handle so far */
 int64_t osgpu_launch_count(osgpu_sim *sim);
 /* cudaStream_t the handle launches on (for CUDA-event timing by the caller) */

@@ -95,9 +95,10 @@ template <typename T> struct Sim final : SimBase {
   size_t xbuf_elems = 0;
   uint32_t *pbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // particle exchange buffers
   int pbuf_rec = 0;
-  cudaEvent_t ev[6];
-  double phase_ms[6] = {0, 0, 0, 0, 0, 0};
+  cudaEvent_t ev[10];  // 0..5 phase boundaries, 6/7 whole call, 8/9 push kernel
+  double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double slack = 0.25;
+  int push_events = 0;
 
   // ---------------------------------------------------------------------------------------
   int init(const osgpu_config *c, const void *nccl_id) {
@@ -542,7 +543,10 @@ template <typename T> struct Sim final : SimBase {
       a.errflag = d_err;
       OSGPU_CUDA(cudaMemsetAsync(s.d_ene, 0, sizeof(double), st));
       OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
+      OSGPU_CUDA(cudaEventRecord(ev[8], st));
       OSGPU_TRY(launch_push_deposit<T>(dim, order, maps, a, tl.ntile, st));
+      OSGPU_CUDA(cudaEventRecord(ev[9], st));
+      push_events++;
       launches += 1;
       s.movers_pending = true;
     }
@@ -634,7 +638,8 @@ template <typename T> struct Sim final : SimBase {
 
   // ---------------------------------------------------------------------------------------
   int step(int nsteps, double *ene) override {
-    for (int k = 0; k < 6; k++) phase_ms[k] = 0;
+    for (int k = 0; k < 8; k++) phase_ms[k] = 0;
+    OSGPU_CUDA(cudaEventRecord(ev[6], st));
     for (int n = 0; n < nsteps; n++) {
       const bool last = (n == nsteps - 1);
       OSGPU_CUDA(cudaEventRecord(ev[0], st));
@@ -642,7 +647,12 @@ template <typename T> struct Sim final : SimBase {
       OSGPU_CUDA(cudaEventRecord(ev[1], st));
       OSGPU_TRY(advance_deposit(nullptr));
       OSGPU_CUDA(cudaEventRecord(ev[2], st));
-      OSGPU_TRY(particles_update_boundary());
+      OSGPU_TRY(particles_update_boundary());  // synchronises (tile-capacity check)
+      if (sp.size() == 1 && sp[0].created) {   // single species: ev[8..9] bracket its one launch
+        float ms = 0;
+        OSGPU_CUDA(cudaEventElapsedTime(&ms, ev[8], ev[9]));
+        phase_ms[6] += ms;
+      }
       OSGPU_CUDA(cudaEventRecord(ev[3], st));
       OSGPU_TRY(current_update_boundary());
       OSGPU_CUDA(cudaEventRecord(ev[4], st));
@@ -656,10 +666,13 @@ template <typename T> struct Sim final : SimBase {
         float ms = 0;
         OSGPU_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
         phase_ms[k] += ms;
-        phase_ms[5] += ms;
       }
     }
+    OSGPU_CUDA(cudaEventRecord(ev[7], st));
     OSGPU_CUDA(cudaStreamSynchronize(st));
+    float tot = 0;
+    OSGPU_CUDA(cudaEventElapsedTime(&tot, ev[6], ev[7]));
+    phase_ms[5] = tot;  // first launch to last completion, gaps included
     return OSGPU_OK;
   }
 
@@ -675,7 +688,7 @@ template <typename T> struct Sim final : SimBase {
     return OSGPU_OK;
   }
   int phase_times(double *out6) override {
-    for (int k = 0; k < 6; k++) out6[k] = phase_ms[k];
+    for (int k = 0; k < 8; k++) out6[k] = phase_ms[k];
     return OSGPU_OK;
   }
 

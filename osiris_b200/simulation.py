@@ -217,10 +217,10 @@ class Simulation:
         return ene
 
     def phase_times_ms(self):
-        out = np.zeros(6, np.float64)
+        out = np.zeros(8, np.float64)
         check(self._L.osgpu_phase_times_ms(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return dict(zip(("update emf boundary", "advance deposit", "update particle boundary",
-                         "update current boundary", "field solver", "loop"), out))
+                         "update current boundary", "field solver", "loop", "push kernel"), [float(v) for v in out]))
 
     @property
     def launch_count(self):

@@ -293,9 +293,12 @@ template <typename T> PIC_HD int split3d(Seg<3, T> *s, const int *di) {
   // x-y-z: x-y logic first, then cut the piece whose z1 left the cell (:591-708)
   split3d_two(s[0], s[1], s[2], 0, 1, di[0], di[1]);
   const T zint = T(0.5) * di[2];
+  bool cut = false;  // unrolled with a flag instead of a break: s[] is only indexed statically
+#pragma unroll
   for (int i = 0; i < 3; i++) {
     Seg<3, T> &a = s[i];
-    if ((a.p1[2] < T(-0.5)) || (a.p1[2] >= T(0.5))) {
+    if (!cut && ((a.p1[2] < T(-0.5)) || (a.p1[2] >= T(0.5)))) {
+      cut = true;
       T delta = (zint - a.p0[2]) / (a.p1[2] - a.p0[2]);
       T xint = lerp(a.p0[0], a.p1[0], delta);
       T yint = lerp(a.p0[1], a.p1[1], delta);
@@ -305,12 +308,12 @@ template <typename T> PIC_HD int split3d(Seg<3, T> *s, const int *di) {
       n.p0[2] = -zint; n.p1[2] = a.p1[2] - di[2];
       n.c[0] = a.c[0]; n.c[1] = a.c[1]; n.c[2] = a.c[2] + di[2];
       a.p1[0] = xint; a.p1[1] = yint; a.p1[2] = zint;
+#pragma unroll
       for (int j = i + 1; j < 3; j++) {
         s[j].p0[2] -= di[2];
         s[j].p1[2] -= di[2];
         s[j].c[2] += di[2];
       }
-      break;
     }
   }
   return 4;

@@ -16,6 +16,12 @@ template <typename T> struct PushArgs {
   MoverView<T> mv;
   const int *tile_off;
   int *tile_cnt;
+  int *tile_nsorted;    // the first tile_nsorted[t] particles of tile t are sorted by cell
+  int *cell_start;      // [ntile][TILE_NCELL + 1] offsets of the cells inside the sorted range
+  SpeciesView<T> scr;   // scratch columns: one range of scr_stride slots per CTA
+  int *scr_rank;
+  int scr_stride;
+  int *tile_counter;    // persistent CTAs take tiles from here (zeroed before the launch)
   T *J[3];
   Grid g;
   Tiling tl;
@@ -25,8 +31,10 @@ template <typename T> struct PushArgs {
 };
 
 template <typename T>
-int launch_push_deposit(int dim, int order, const TmaMaps &maps, const PushArgs<T> &a, int ntile,
+int launch_push_deposit(int dim, int order, const TmaMaps &maps, const PushArgs<T> &a, int nblocks,
                         cudaStream_t st);
+// resident CTAs per SM of the kernel for (dim, order)
+template <typename T> int push_blocks_per_sm(int dim, int order);
 // TMA box (elements, fastest first) and dynamic shared memory of the kernel for (dim, order)
 template <typename T> void push_tile_shape(int dim, int order, int *box, int *smem_bytes);
 

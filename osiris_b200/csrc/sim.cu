@@ -80,6 +80,10 @@ template <typename T> struct Sim final : SimBase {
     int cur = 0;
     int *tile_off[2] = {nullptr, nullptr};  // ntile + 1
     int *tile_cnt = nullptr, *tile_arr = nullptr;
+    int *tile_nsorted = nullptr;  // leading particles of each tile that are sorted by cell
+    int *cell_start = nullptr;    // [ntile][TILE_NCELL + 1] cell offsets inside the sorted range
+    int *tile_counter = nullptr;  // work counter of the persistent push CTAs
+    int max_range = 0;            // widest tile slot range of the current layout
     MoverView<T> mv;
     void *mvmem = nullptr;
     double *d_ene = nullptr;
@@ -99,6 +103,7 @@ template <typename T> struct Sim final : SimBase {
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double slack = 0.25;
   int push_events = 0;
+  int n_sm = 1, push_bps = 1;  // SMs, resident push CTAs per SM
 
   // ---------------------------------------------------------------------------------------
   int init(const osgpu_config *c, const void *nccl_id) {
@@ -169,6 +174,8 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaMalloc(&d_fe, 6 * sizeof(double)));
     OSGPU_CUDA(cudaHostAlloc(&h_pin, 16 * sizeof(int), cudaHostAllocDefault));
     OSGPU_TRY(make_tensor_maps());
+    OSGPU_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    push_bps = push_blocks_per_sm<T>(dim, order);
 
     // neighbours (t_node_conf%neighbor, os-nconf.f03:1101-1112)
     int nb[6];
@@ -237,9 +244,10 @@ template <typename T> struct Sim final : SimBase {
   }
 
   // ---------------------------------------------------------------------------------------
-  static size_t species_bytes(int dim, long long cap) {
-    return (size_t)cap * ((dim + 4) * sizeof(T) + sizeof(int) + sizeof(long long));
-  }
+  // per slot: x(D) p(3) q, packed cell, tag, + one int (the rank column when the buffer serves as
+  // the push kernel's scratch)
+  static size_t slot_bytes(int dim) { return (dim + 4) * sizeof(T) + 2 * sizeof(int) + sizeof(long long); }
+  static size_t species_bytes(int dim, long long cap) { return (size_t)cap * slot_bytes(dim); }
   static void carve(void *mem, int dim, long long cap, SpeciesView<T> *v) {
     char *p = (char *)mem;
     v->tag = (long long *)p; p += cap * sizeof(long long);
@@ -250,6 +258,10 @@ template <typename T> struct Sim final : SimBase {
     for (int d = 0; d < 3; d++) { v->p[d] = (T *)p; p += cap * sizeof(T); }
     v->q = (T *)p; p += cap * sizeof(T);
     v->cell = (int *)p;
+  }
+  // the same memory seen as `cap` scratch slots with a rank column
+  static int *carve_rank(void *mem, int dim, long long cap) {
+    return (int *)((char *)mem + (size_t)cap * (slot_bytes(dim) - sizeof(int)));
   }
 
   int species_create(int id, double rqm, long long np_max) override {
@@ -268,6 +280,10 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaMalloc(&s.tile_cnt, sizeof(int) * tl.ntile));
     OSGPU_CUDA(cudaMalloc(&s.tile_arr, sizeof(int) * tl.ntile));
     OSGPU_CUDA(cudaMemsetAsync(s.tile_cnt, 0, sizeof(int) * tl.ntile, st));
+    OSGPU_CUDA(cudaMalloc(&s.tile_nsorted, sizeof(int) * tl.ntile));
+    OSGPU_CUDA(cudaMemsetAsync(s.tile_nsorted, 0, sizeof(int) * tl.ntile, st));
+    OSGPU_CUDA(cudaMalloc(&s.cell_start, sizeof(int) * (size_t)tl.ntile * (pic::TILE_NCELL + 1)));
+    OSGPU_CUDA(cudaMalloc(&s.tile_counter, sizeof(int)));
     // mover buffer: a quarter of the particles may change tile in one step before this overflows
     long long mcap = std::max<long long>(np_max / 4 + 4096, 65536);
     if (mcap > np_max + 4096) mcap = np_max + 4096;
@@ -302,17 +318,23 @@ template <typename T> struct Sim final : SimBase {
 
   // tile ranges from per-tile counts: every range is a multiple of 32 slots (128-byte aligned
   // fp32 columns) with `slack` spare room; shrinks the slack until the total fits.
-  int layout_offsets(const std::vector<int> &need, long long cap, std::vector<int> *off) {
+  int layout_offsets(const std::vector<int> &need, long long cap, std::vector<int> *off, int *max_range) {
     double sl = slack;
     off->resize(need.size() + 1);
     for (int it = 0; it < 8; it++) {
-      long long tot = 0;
+      long long tot = 0, widest = 32;
       for (size_t t = 0; t < need.size(); t++) {
         (*off)[t] = (int)tot;
         long long c = need[t] + (long long)(need[t] * sl) + (sl > 0 ? 32 : 0);
-        tot += (c + 31) / 32 * 32;
+        c = (c + 31) / 32 * 32;
+        widest = std::max(widest, c);
+        tot += c;
       }
-      if (tot <= cap && tot < 0x7fffffffll) { (*off)[need.size()] = (int)tot; return OSGPU_OK; }
+      if (tot <= cap && tot < 0x7fffffffll) {
+        (*off)[need.size()] = (int)tot;
+        *max_range = (int)widest;
+        return OSGPU_OK;
+      }
       sl = (it == 6) ? 0.0 : sl * 0.5;
     }
     set_error("particle buffer too small: capacity %lld slots", cap);
@@ -376,8 +398,9 @@ template <typename T> struct Sim final : SimBase {
         break;
       }
       if ((rc = check_err("species_upload")) != OSGPU_OK) break;
-      if ((rc = layout_offsets(cnt, s.cap, &off)) != OSGPU_OK) break;
+      if ((rc = layout_offsets(cnt, s.cap, &off, &s.max_range)) != OSGPU_OK) break;
       s.cur = 0;
+      cudaMemsetAsync(s.tile_nsorted, 0, sizeof(int) * tl.ntile, st);  // bin_scatter leaves tiles unsorted
       cudaMemcpyAsync(s.tile_off[0], off.data(), sizeof(int) * (tl.ntile + 1), cudaMemcpyHostToDevice, st);
       cudaMemsetAsync(s.tile_arr, 0, sizeof(int) * tl.ntile, st);  // used as the scatter cursor
       if ((rc = bin_scatter<T>(in, np, 0, g, tl, s.tile_off[0], s.tile_arr, s.v[0], st, &launches)) != OSGPU_OK) break;
@@ -531,6 +554,17 @@ template <typename T> struct Sim final : SimBase {
       a.mv = s.mv;
       a.tile_off = s.tile_off[s.cur];
       a.tile_cnt = s.tile_cnt;
+      a.tile_nsorted = s.tile_nsorted;
+      a.cell_start = s.cell_start;
+      a.tile_counter = s.tile_counter;
+      // persistent CTAs; each owns one scratch range (widest tile) carved from the idle buffer
+      int nblocks = std::min(tl.ntile, n_sm * push_bps);
+      while (nblocks > 1 && (long long)nblocks * s.max_range > s.cap) nblocks--;
+      const long long nscr = (long long)nblocks * s.max_range;
+      carve(s.mem[1 - s.cur], dim, nscr, &a.scr);
+      a.scr_rank = carve_rank(s.mem[1 - s.cur], dim, nscr);
+      a.scr_stride = s.max_range;
+      OSGPU_CUDA(cudaMemsetAsync(s.tile_counter, 0, sizeof(int), st));
       for (int k = 0; k < 3; k++) a.J[k] = J.c[k];
       a.g = g;
       a.tl = tl;
@@ -544,7 +578,7 @@ template <typename T> struct Sim final : SimBase {
       OSGPU_CUDA(cudaMemsetAsync(s.d_ene, 0, sizeof(double), st));
       OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
       OSGPU_CUDA(cudaEventRecord(ev[8], st));
-      OSGPU_TRY(launch_push_deposit<T>(dim, order, maps, a, tl.ntile, st));
+      OSGPU_TRY(launch_push_deposit<T>(dim, order, maps, a, nblocks, st));
       OSGPU_CUDA(cudaEventRecord(ev[9], st));
       push_events++;
       launches += 1;
@@ -594,7 +628,7 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaStreamSynchronize(st));
     std::vector<int> need(tl.ntile);
     for (int t = 0; t < tl.ntile; t++) need[t] = cnt[t] + arr[t];
-    OSGPU_TRY(layout_offsets(need, s.cap, &off));
+    OSGPU_TRY(layout_offsets(need, s.cap, &off, &s.max_range));
     const int nxt = 1 - s.cur;
     OSGPU_CUDA(cudaMemcpyAsync(s.tile_off[nxt], off.data(), sizeof(int) * (tl.ntile + 1), cudaMemcpyHostToDevice, st));
     OSGPU_TRY(relayout<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, s.v[nxt], s.tile_off[nxt], g, tl, st, &launches));
@@ -697,6 +731,7 @@ template <typename T> struct Sim final : SimBase {
     for (auto &s : sp) {
       for (int k = 0; k < 2; k++) { cudaFree(s.mem[k]); cudaFree(s.tile_off[k]); }
       cudaFree(s.tile_cnt); cudaFree(s.tile_arr); cudaFree(s.mvmem); cudaFree(s.d_ene);
+      cudaFree(s.tile_nsorted); cudaFree(s.cell_start); cudaFree(s.tile_counter);
     }
     for (auto &b : xbuf) cudaFree(b);
     for (auto &b : pbuf) cudaFree(b);

@@ -1,6 +1,7 @@
 // tile.cuh -- cell-tile geometry shared by the kernels and the host-side layout code.
 //
-// Particles are binned into tiles of TX x TY (x TZ) cells.  One CTA owns one tile: it stages
+// Particles are binned into tiles of TX x TY (x TZ) cells (16 x 16 in 2D, 8 x 8 x 4 in 3D: 256 cells,
+// one per thread of the CTA that owns the tile).  One CTA owns one tile: it stages
 // the E/B values every particle of the tile can touch into shared memory (tile + stencil halo),
 // accumulates the tile's current into a shared-memory J tile (tile + stencil halo + one cell of
 // motion), and writes that back once.
@@ -16,7 +17,8 @@ template <int DIM, int ORDER, typename T> struct Tile {
   static constexpr int NP = S::NP, LP = S::LP;
   static constexpr int TX = (DIM == 2) ? 16 : 8;
   static constexpr int TY = (DIM == 2) ? 16 : 8;
-  static constexpr int TZ = (DIM == 2) ? 1 : 8;
+  static constexpr int TZ = (DIM == 2) ? 1 : 4;
+  static constexpr int NCELL = TX * TY * TZ;  // 256 in both geometries
   // E/B tile: interpolation points l+LP-1 .. l+UP for every local cell l in [0,T)
   static constexpr int EX = TX + NP, EY = TY + NP, EZ = (DIM == 3) ? TZ + NP : 1;
   // inner extent padded so a TMA box row is a multiple of 16 bytes
@@ -33,7 +35,8 @@ template <int DIM, int ORDER, typename T> struct Tile {
 };
 
 // tile edge used by the host-side layout code for a given dimensionality
-inline int tile_edge(int dim, int axis) { return (dim == 2) ? (axis < 2 ? 16 : 1) : 8; }
+inline int tile_edge(int dim, int axis) { return (dim == 2) ? (axis < 2 ? 16 : 1) : (axis < 2 ? 8 : 4); }
+constexpr int TILE_NCELL = 256;
 
 // packed per-particle cell word: (l_d + 1) in 10-bit fields, bit 31 = particle left the tile
 constexpr int CELL_BITS = 10;
@@ -51,14 +54,14 @@ template <typename T> struct PushConst {
 };
 
 // ------------------------------------------------------------------------------------------
-// One particle: interpolate E,B from the tile, Boris, move, trim, split, deposit into the J
-// tile.  x[], u[] and l[] are advanced in place; l[] may leave [0,T) by one cell.
+// One particle, first half: interpolate E,B from the tile, Boris, move, trim, split.
+// x[], u[] and l[] are advanced in place; l[] may leave [0,T) by one cell.  seg[0..nseg) are
+// the trajectory pieces (each inside one cell); returns u^2/(gamma+1) of the centred momentum.
 // Statement order follows ADVANCE_DEPOSIT_2D/3D (simd/os-spec-push-avx2.c:471-760, 1141-1472).
-// `add(ptr, v)` accumulates into the J tile (shared-memory atomic on the device).
 // ------------------------------------------------------------------------------------------
-template <int DIM, int ORDER, typename T, class Add>
-PIC_HD T push_deposit_one(T *x, T *u, T q, int *l, const T *eb, T *jt, const PushConst<T> &k,
-                          Add add) {
+template <int DIM, int ORDER, typename T>
+PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DIM, T> *seg,
+                  int *nseg_out) {
   using G = Tile<DIM, ORDER, T>;
   constexpr int NP = G::NP;
   T w[DIM][NP], wh[DIM][NP];
@@ -120,7 +123,6 @@ PIC_HD T push_deposit_one(T *x, T *u, T q, int *l, const T *eb, T *jt, const Pus
   const T ene = boris<T>(k.tem, f[0], f[1], f[2], f[3], f[4], f[5], u);
   const T rg = rgamma<T>(u);
 
-  Seg<DIM, T> seg[DIM + 1];
   int di[3] = {0, 0, 0};
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
@@ -132,77 +134,136 @@ PIC_HD T push_deposit_one(T *x, T *u, T q, int *l, const T *eb, T *jt, const Pus
     x[d] = x1 - T(di[d]);
     l[d] += di[d];
   }
-  int nseg;
   if constexpr (DIM == 2) {
     seg[0].vz = u[2] * rg;
-    nseg = split2d<T>(seg, di[0], di[1]);
+    *nseg_out = split2d<T>(seg, di[0], di[1]);
   } else {
-    nseg = split3d<T>(seg, di);
+    *nseg_out = split3d<T>(seg, di);
   }
+  return ene;
+}
 
-  // deposit (DEP_CURRENT_2D/3D, simd/os-spec-current-avx2.c:730-865, 1147-1318)
-  for (int s = 0; s < nseg; s++) {
-    const Seg<DIM, T> &a = seg[s];
-    T s0[DIM][NP], s1[DIM][NP], wlv[DIM][NP];
+// Esirkepov weights of one segment (DEP_CURRENT_2D/3D, simd/os-spec-current-avx2.c:730-865,
+// 1147-1318): calls out(comp, k1, k2, k3, f1, f2) for every non-zero stencil entry, whose value is
+// f1 * f2; the entry belongs to grid point (cell + k + LP) of component comp.
+template <int DIM, int ORDER, typename T, class Out>
+PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Out out) {
+  constexpr int NP = Stencil<ORDER>::NP;
+  T s0[DIM][NP], s1[DIM][NP], wlv[DIM][NP];
 #pragma unroll
-    for (int d = 0; d < DIM; d++) {
-      spline<ORDER, T>(a.p0[d], s0[d]);
-      spline<ORDER, T>(a.p1[d], s1[d]);
-      wl<ORDER, T>(q * k.jnorm[d], a.p0[d], a.p1[d], wlv[d]);
-    }
-    if constexpr (DIM == 2) {
-      const T qvz = (q * a.vz) * (T(1.0) / T(3.0));
-      T *pj = jt + (a.c[0] + 1) + G::JX * (a.c[1] + 1);
+  for (int d = 0; d < DIM; d++) {
+    spline<ORDER, T>(a.p0[d], s0[d]);
+    spline<ORDER, T>(a.p1[d], s1[d]);
+    wl<ORDER, T>(q * k.jnorm[d], a.p0[d], a.p1[d], wlv[d]);
+  }
+  if constexpr (DIM == 2) {
+    const T qvz = (q * a.vz) * (T(1.0) / T(3.0));
 #pragma unroll
-      for (int k2 = 0; k2 < NP; k2++) {
-        const T wp1 = s0[1][k2] + s1[1][k2];
+    for (int k2 = 0; k2 < NP; k2++) {
+      const T wp1 = s0[1][k2] + s1[1][k2];
 #pragma unroll
-        for (int k1 = 0; k1 < NP; k1++) {
-          const T wp2 = s0[0][k1] + s1[0][k1];
-          T *c = pj + k1 + G::JX * k2;
-          if (k1 < NP - 1) add(c, wlv[0][k1] * wp1);
-          if (k2 < NP - 1) add(c + G::JVOL, wlv[1][k2] * wp2);
-          const T s00 = s0[0][k1] * s0[1][k2];
-          T tmp1 = fmadd(s1[1][k2], s1[0][k1], s00);
-          const T s10 = s0[0][k1] * s1[1][k2];
-          const T tmp2 = fmadd(s0[1][k2], s1[0][k1], s10);
-          tmp1 = fmadd(tmp2, T(0.5), tmp1);
-          add(c + 2 * G::JVOL, qvz * tmp1);
-        }
+      for (int k1 = 0; k1 < NP; k1++) {
+        const T wp2 = s0[0][k1] + s1[0][k1];
+        if (k1 < NP - 1) out(0, k1, k2, 0, wlv[0][k1], wp1);
+        if (k2 < NP - 1) out(1, k1, k2, 0, wlv[1][k2], wp2);
+        const T s00 = s0[0][k1] * s0[1][k2];
+        T tmp1 = fmadd(s1[1][k2], s1[0][k1], s00);
+        const T s10 = s0[0][k1] * s1[1][k2];
+        const T tmp2 = fmadd(s0[1][k2], s1[0][k1], s10);
+        tmp1 = fmadd(tmp2, T(0.5), tmp1);
+        out(2, k1, k2, 0, qvz, tmp1);
       }
-    } else {
-      constexpr int Z = DIM - 1;  // == 2; written this way so the 2D instantiation compiles
-      T *pj = jt + (a.c[0] + 1) + G::JX * ((a.c[1] + 1) + G::JY * (a.c[Z] + 1));
-      // wp?[kb][ka] as in the reference: wp1[kz][ky], wp2[kz][kx], wp3[ky][kx]
-      T wp1[NP][NP], wp2[NP][NP], wp3[NP][NP];
+    }
+  } else {
+    constexpr int Z = DIM - 1;  // == 2; written this way so the 2D instantiation compiles
+    // wp?[kb][ka] as in the reference: wp1[kz][ky], wp2[kz][kx], wp3[ky][kx]
+    T wp1[NP][NP], wp2[NP][NP], wp3[NP][NP];
+#pragma unroll
+    for (int k2 = 0; k2 < NP; k2++)
+#pragma unroll
+      for (int k1 = 0; k1 < NP; k1++) {
+        T t1, t2;
+        t1 = s0[1][k1] * s0[Z][k2]; t2 = s0[1][k1] * s1[Z][k2];
+        t1 = fmadd(s1[1][k1], s1[Z][k2], t1); t2 = fmadd(s1[1][k1], s0[Z][k2], t2);
+        wp1[k2][k1] = fmadd(T(0.5), t2, t1);
+        t1 = s0[0][k1] * s0[Z][k2]; t2 = s0[0][k1] * s1[Z][k2];
+        t1 = fmadd(s1[0][k1], s1[Z][k2], t1); t2 = fmadd(s1[0][k1], s0[Z][k2], t2);
+        wp2[k2][k1] = fmadd(T(0.5), t2, t1);
+        t1 = s0[0][k1] * s0[1][k2]; t2 = s0[0][k1] * s1[1][k2];
+        t1 = fmadd(s1[0][k1], s1[1][k2], t1); t2 = fmadd(s1[0][k1], s0[1][k2], t2);
+        wp3[k2][k1] = fmadd(T(0.5), t2, t1);
+      }
+#pragma unroll
+    for (int k3 = 0; k3 < NP; k3++)
 #pragma unroll
       for (int k2 = 0; k2 < NP; k2++)
 #pragma unroll
         for (int k1 = 0; k1 < NP; k1++) {
-          T t1, t2;
-          t1 = s0[1][k1] * s0[Z][k2]; t2 = s0[1][k1] * s1[Z][k2];
-          t1 = fmadd(s1[1][k1], s1[Z][k2], t1); t2 = fmadd(s1[1][k1], s0[Z][k2], t2);
-          wp1[k2][k1] = fmadd(T(0.5), t2, t1);
-          t1 = s0[0][k1] * s0[Z][k2]; t2 = s0[0][k1] * s1[Z][k2];
-          t1 = fmadd(s1[0][k1], s1[Z][k2], t1); t2 = fmadd(s1[0][k1], s0[Z][k2], t2);
-          wp2[k2][k1] = fmadd(T(0.5), t2, t1);
-          t1 = s0[0][k1] * s0[1][k2]; t2 = s0[0][k1] * s1[1][k2];
-          t1 = fmadd(s1[0][k1], s1[1][k2], t1); t2 = fmadd(s1[0][k1], s0[1][k2], t2);
-          wp3[k2][k1] = fmadd(T(0.5), t2, t1);
+          if (k1 < NP - 1) out(0, k1, k2, k3, wlv[0][k1], wp1[k3][k2]);
+          if (k2 < NP - 1) out(1, k1, k2, k3, wlv[1][k2], wp2[k3][k1]);
+          if (k3 < NP - 1) out(2, k1, k2, k3, wlv[Z][k3], wp3[k2][k1]);
         }
-#pragma unroll
-      for (int k3 = 0; k3 < NP; k3++)
-#pragma unroll
-        for (int k2 = 0; k2 < NP; k2++)
-#pragma unroll
-          for (int k1 = 0; k1 < NP; k1++) {
-            T *c = pj + k1 + G::JX * (k2 + G::JY * k3);
-            if (k1 < NP - 1) add(c, wlv[0][k1] * wp1[k3][k2]);
-            if (k2 < NP - 1) add(c + G::JVOL, wlv[1][k2] * wp2[k3][k1]);
-            if (k3 < NP - 1) add(c + 2 * G::JVOL, wlv[Z][k3] * wp3[k2][k1]);
-          }
-    }
   }
+}
+
+// the (comp, k1, k2, k3) of every non-zero stencil entry, in segment_current's order
+template <int DIM, int ORDER, class F> PIC_HD void for_each_stencil_entry(F f) {
+  constexpr int NP = Stencil<ORDER>::NP;
+  constexpr int NZ = (DIM == 3) ? NP : 1;
+#pragma unroll
+  for (int k3 = 0; k3 < NZ; k3++)
+#pragma unroll
+    for (int k2 = 0; k2 < NP; k2++)
+#pragma unroll
+      for (int k1 = 0; k1 < NP; k1++) {
+        if (k1 < NP - 1) f(0, k1, k2, k3);
+        if (k2 < NP - 1) f(1, k1, k2, k3);
+        if (DIM == 2 || k3 < NP - 1) f(2, k1, k2, k3);
+      }
+}
+
+// first J-tile element of the stencil of a segment in tile-local cell c[]
+template <int DIM, int ORDER, typename T> PIC_HD int jtile_base(const int *c) {
+  using G = Tile<DIM, ORDER, T>;
+  if constexpr (DIM == 2) return (c[0] + 1) + G::JX * (c[1] + 1);
+  else return (c[0] + 1) + G::JX * ((c[1] + 1) + G::JY * (c[DIM - 1] + 1));
+}
+
+// deposit one segment straight into the J tile; `add(ptr, v)` accumulates (shared-memory atomic
+// on the device)
+template <int DIM, int ORDER, typename T, class Add>
+PIC_HD void deposit_segment(const Seg<DIM, T> &a, T q, T *jt, const PushConst<T> &k, Add add) {
+  using G = Tile<DIM, ORDER, T>;
+  T *pj = jt + jtile_base<DIM, ORDER, T>(a.c);
+  segment_current<DIM, ORDER, T>(a, q, k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
+    add(pj + comp * G::JVOL + k1 + G::JX * (k2 + G::JY * k3), f1 * f2);
+  });
+}
+
+// deposit the segments selected by `mask`; the segment is picked with selects so that seg[] can
+// stay in registers (no dynamically indexed local array)
+template <int DIM, int ORDER, typename T, class Add>
+PIC_HD void deposit_segments(const Seg<DIM, T> *seg, int nseg, unsigned mask, T q, T *jt,
+                             const PushConst<T> &k, Add add) {
+#pragma unroll 1
+  for (int s = 0; s < nseg; s++) {
+    if (!((mask >> s) & 1u)) continue;
+    Seg<DIM, T> sg = seg[0];
+#pragma unroll
+    for (int m = 1; m <= DIM; m++)
+      if (s == m) sg = seg[m];
+    deposit_segment<DIM, ORDER, T>(sg, q, jt, k, add);
+  }
+}
+
+// One particle, both halves (push_one + deposit of every segment).
+template <int DIM, int ORDER, typename T, class Add>
+PIC_HD T push_deposit_one(T *x, T *u, T q, int *l, const T *eb, T *jt, const PushConst<T> &k,
+                          Add add) {
+  Seg<DIM, T> seg[DIM + 1];
+  int nseg;
+  const T ene = push_one<DIM, ORDER, T>(x, u, l, eb, k, seg, &nseg);
+  deposit_segments<DIM, ORDER, T>(seg, nseg, 0xf, q, jt, k, add);
   return ene;
 }
 

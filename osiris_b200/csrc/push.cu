@@ -109,10 +109,11 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr bool FAST = ORDER <= 2;
   static constexpr int DW = (DIM == 2) ? 6 : 7;  // parked trajectory: x0[D], x1[D], q, (vz)
   static constexpr int XW = DW + 1;              // listed piece: + packed tile-local cell
-  static constexpr int BUF_BYTES = FAST ? 67584 : 0;
-  static constexpr int XMIN_BYTES = 10240;  // room always left for the list
-  static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
-  static constexpr int DCAP = FAST ? (((BUF_BYTES - XMIN_BYTES) / (DW * (int)sizeof(T))) & ~31) : 0;
+  // one private buffer per warp: parked trajectories from the bottom, the list above them
+  static constexpr int BUF_BYTES = FAST ? 76800 : 0;
+  static constexpr int WARP_WORDS = BUF_BYTES / (int)sizeof(T) / (NTHREADS / 32);
+  static constexpr int XMIN = 40;  // list entries always available
+  static constexpr int PCAP = FAST ? (((WARP_WORDS - XMIN * XW) / DW) & ~31) : 32;
   static constexpr int NACC = 3 * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
   static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
   static constexpr int OFF_BUF = OFF_JT + round_up(3 * G::JVOL * (int)sizeof(T), 16);
@@ -130,6 +131,53 @@ template <int DIM> __device__ __forceinline__ int linear_cell(const int *l) {
   else return l[0] + G::TX * (l[1] + G::TY * l[DIM - 1]);
 }
 
+// Flush of the per-cell stencil accumulators when the 32 lanes of a warp hold 32 consecutive cells
+// (rows of TX cells along x).  The stencils of x-neighbours overlap: the lane that owns a grid
+// column (the one whose entry k1 = KO lands there) collects its neighbours' entries for that
+// column with shuffles and issues the only shared-memory atomic; entries whose owner would lie
+// outside the row are added by the lane itself.
+template <int DIM, int ORDER, typename T, class P>
+__device__ __forceinline__ void flush_merged(const T *acc, T *pj, int x) {
+  using G = Tile<DIM, ORDER, T>;
+  constexpr int NP = G::NP;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NZ = (DIM == 3) ? NP : 1;
+#pragma unroll
+  for (int comp = 0; comp < 3; comp++) {
+    constexpr int dummy = 0;
+    (void)dummy;
+#pragma unroll
+    for (int k3 = 0; k3 < NZ; k3++) {
+#pragma unroll
+      for (int k2 = 0; k2 < NP; k2++) {
+        if (comp == 1 && k2 >= NP - 1) continue;
+        if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
+        const int nk1 = (comp == 0) ? NP - 1 : NP;  // entries along x
+        const int ko = (nk1 - 1 < 1) ? nk1 - 1 : 1; // owner entry
+        T *row = pj + comp * G::JVOL + G::JX * (k2 + G::JY * k3);
+        T m = acc[P::acc_index(comp, ko, k2, k3)];
+#pragma unroll
+        for (int d = 1; d <= ko; d++) {  // entry ko - d of the lane d cells to the right
+          const T t = __shfl_down_sync(FULL, acc[P::acc_index(comp, ko - d, k2, k3)], d);
+          if (x + d < G::TX) m += t;
+        }
+#pragma unroll
+        for (int d = 1; d <= nk1 - 1 - ko; d++) {  // entry ko + d of the lane d cells to the left
+          const T t = __shfl_up_sync(FULL, acc[P::acc_index(comp, ko + d, k2, k3)], d);
+          if (x - d >= 0) m += t;
+        }
+        atomicAdd(row + ko, m);
+#pragma unroll
+        for (int k1 = 0; k1 < nk1; k1++) {
+          if (k1 == ko) continue;
+          const int xo = x + k1 - ko;  // owner cell of this column
+          if (xo < 0 || xo >= G::TX) atomicAdd(row + k1, acc[P::acc_index(comp, k1, k2, k3)]);
+        }
+      }
+    }
+  }
+}
+
 template <int DIM, int ORDER, typename T>
 __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2)
     push_deposit_kernel(const __grid_constant__ TmaMaps maps, const PushArgs<T> a) {
@@ -142,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   int *cs = reinterpret_cast<int *>(smem_raw + P::OFF_CS);
   int *hist = reinterpret_cast<int *>(smem_raw + P::OFF_HIST);
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ int s_tile, s_nx[2], s_mcnt, s_base;
+  __shared__ int s_tile, s_mcnt, s_base;
   __shared__ int s_warp[NTHREADS / 32];
   __shared__ double s_ene[NTHREADS / 32];
 
@@ -188,8 +236,6 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
 
     // ---- 0. stage E/B, clear J tile and histogram ------------------------------------------
     if (tid == 0) {
-      s_nx[0] = 0;
-      s_nx[1] = 0;
       s_mcnt = 0;
       mbar_expect_tx(&mbar, 6u * (uint32_t)(G::EVOL * sizeof(T)));
       const int c0 = o0[0] + a.g.gl[0] + G::HALO_LO;
@@ -212,70 +258,102 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     mbar_wait(&mbar, phase);
     phase ^= 1;
 
-    // ---- 1..3: pieces of the sorted range, then the unsorted tail --------------------------
-    int p0 = 0, piece = 0;
-    while (p0 < n) {
-      const bool sorted = P::FAST && (p0 < ns);
-      const int p1 = sorted ? min(ns, p0 + P::DCAP) : n;
-      const int np = p1 - p0;
-      // shared list of neighbour-cell pieces: whatever the parked trajectories leave free
-      T *xl = buf + P::DW * np;
-      const int xcap = sorted ? (P::BUF_WORDS - P::DW * np) / P::XW : 0;
+    // ---- 1..3: every warp works through its own 32 cells without CTA-wide barriers --------
+    {
+      constexpr unsigned FULL = 0xffffffffu;
+      const unsigned lt_mask = (1u << lane) - 1u;
+      const int c_lo = 32 * wid;
+      // sorted particles of this warp's cells, and its share of the unsorted tail
+      const int sa = (ns > 0) ? cs[c_lo] : 0, sb = (ns > 0) ? cs[c_lo + 32] : 0;
+      const int tchunk = (n - ns + NTHREADS / 32 - 1) / (NTHREADS / 32);
+      const int ta = min(n, ns + wid * tchunk), tb = min(n, ta + tchunk);
+      T *wbuf = buf + wid * P::WARP_WORDS;
 
-      // -- 1. push ---------------------------------------------------------------------------
-      for (int i = p0 + tid; i < p1; i += NTHREADS) {
-        const long long s = off + i;
-        T x[DIM], u[3];
-        int l[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; d++) x[d] = a.sp.x[d][s];
-#pragma unroll
-        for (int d = 0; d < 3; d++) u[d] = a.sp.p[d][s];
-        const T q = a.sp.q[s];
-        const int cell = a.sp.cell[s];
-        const long long tag = a.sp.tag[s];
-#pragma unroll
-        for (int d = 0; d < DIM; d++) l[d] = cell_l(cell, d);
-        Seg<DIM, T> seg[DIM + 1];
-        int nseg;
-        const T en = push_one<DIM, ORDER, T>(x, u, l, eb, a.k, seg, &nseg);
-        ene += (double)q * (double)en;
-        bool moved = false;
-        int ncell = 0;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-          moved |= (l[d] < 0) || (l[d] >= tlim[d]);
-          ncell |= (l[d] + 1) << (d * CELL_BITS);
-        }
-        if (DIM == 2) ncell |= 1 << (2 * CELL_BITS);
-        int rank = 0;
-        if (moved) ncell |= CELL_DEAD;
-        else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
-        const long long r = so + i;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) a.scr.x[d][r] = x[d];
-#pragma unroll
-        for (int d = 0; d < 3; d++) a.scr.p[d][r] = u[d];
-        a.scr.q[r] = q;
-        a.scr.cell[r] = ncell;
-        a.scr.tag[r] = tag;
-        a.scr_rank[r] = rank;
+      int pa = sa;
+      do {
+        const int pb = min(sb, pa + P::PCAP);
+        const int np = pb - pa;                       // parked trajectories of this piece
+        const int tot = np + ((pb == sb) ? tb - ta : 0);  // the last piece also takes the tail share
+        T *xl = wbuf + P::DW * np;                    // list of pieces to deposit one by one
+        const int xcap = (P::WARP_WORDS - P::DW * np) / P::XW;
+        int nxw = 0;                                  // warp-uniform list length
 
-        if (sorted) {
-          const int j = i - p0;
+        // -- 1. push, 32 particles per round; the next round's loads are issued first ----------
+        T nx_[DIM], nu_[3], nq_ = T(0);
+        int ncell_ = 0;
+        long long ntag_ = 0;
+        auto fetch = [&](int m) {
+          if (m < tot) {
+            const long long s = off + ((m < np) ? pa + m : ta + (m - np));
 #pragma unroll
-          for (int d = 0; d < DIM; d++) {
-            buf[d * np + j] = seg[0].p0[d];
-            buf[(DIM + d) * np + j] = seg[0].p1[d];
+            for (int d = 0; d < DIM; d++) nx_[d] = a.sp.x[d][s];
+#pragma unroll
+            for (int d = 0; d < 3; d++) nu_[d] = a.sp.p[d][s];
+            nq_ = a.sp.q[s];
+            ncell_ = a.sp.cell[s];
+            ntag_ = a.sp.tag[s];
           }
-          buf[2 * DIM * np + j] = q;
-          if (DIM == 2) buf[(2 * DIM + 1) * np + j] = seg[0].vz;
-          unsigned direct = 0;  // pieces the list had no room for
+        };
+        fetch(lane);
+        for (int m0 = 0; m0 < tot; m0 += 32) {
+          const int m = m0 + lane;
+          const bool active = m < tot, parked = m < np;
+          T x[DIM], u[3];
 #pragma unroll
-          for (int k = 1; k <= DIM; k++) {
-            if (k < nseg) {
-              const int e = atomicAdd(&s_nx[piece & 1], 1);
-              if (e < xcap) {
+          for (int d = 0; d < DIM; d++) x[d] = nx_[d];
+#pragma unroll
+          for (int d = 0; d < 3; d++) u[d] = nu_[d];
+          const T q = nq_;
+          const int cell = ncell_;
+          const long long tag = ntag_;
+          fetch(m + 32);
+          Seg<DIM, T> seg[DIM + 1];
+          int nseg = 0;
+          if (active) {
+            int l[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) l[d] = cell_l(cell, d);
+            const T en = push_one<DIM, ORDER, T>(x, u, l, eb, a.k, seg, &nseg);
+            ene += (double)q * (double)en;
+            bool moved = false;
+            int ncell = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+              moved |= (l[d] < 0) || (l[d] >= tlim[d]);
+              ncell |= (l[d] + 1) << (d * CELL_BITS);
+            }
+            if (DIM == 2) ncell |= 1 << (2 * CELL_BITS);
+            int rank = 0;
+            if (moved) ncell |= CELL_DEAD;
+            else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
+            const long long r = so + ((m < np) ? pa + m : ta + (m - np));
+#pragma unroll
+            for (int d = 0; d < DIM; d++) a.scr.x[d][r] = x[d];
+#pragma unroll
+            for (int d = 0; d < 3; d++) a.scr.p[d][r] = u[d];
+            a.scr.q[r] = q;
+            a.scr.cell[r] = ncell;
+            a.scr.tag[r] = tag;
+            a.scr_rank[r] = rank;
+            if (P::FAST && parked) {
+#pragma unroll
+              for (int d = 0; d < DIM; d++) {
+                wbuf[d * np + m] = seg[0].p0[d];
+                wbuf[(DIM + d) * np + m] = seg[0].p1[d];
+              }
+              wbuf[2 * DIM * np + m] = q;
+              if (DIM == 2) wbuf[(2 * DIM + 1) * np + m] = seg[0].vz;
+            }
+          }
+          // pieces in neighbouring cells (and every piece of a tail particle) go to the list
+          unsigned direct = 0;
+#pragma unroll
+          for (int k = 0; k <= DIM; k++) {
+            const bool has = active && (k < nseg) && (k > 0 || !(P::FAST && parked));
+            const unsigned hm = __ballot_sync(FULL, has);
+            if (has) {
+              const int e = nxw + __popc(hm & lt_mask);
+              if (P::FAST && e < xcap) {
 #pragma unroll
                 for (int d = 0; d < DIM; d++) {
                   xl[d * xcap + e] = seg[k].p0[d];
@@ -291,67 +369,63 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
                 direct |= 1u << k;
               }
             }
+            nxw += __popc(hm);
           }
           if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
-        } else {
-          deposit_segments<DIM, ORDER, T>(seg, nseg, 0xfu, q, jt, a.k, atomic_add);
         }
-      }
 
-      if constexpr (P::FAST) {
-        if (sorted) {
-          __syncthreads();
-          // -- 2. deposit, one thread per (cell, part): stencil accumulated in registers ---------
-          // cells that overlap [p0, p1): ca = cell of particle p0, cb = cell of particle p1 - 1
-          int ca, cb;
-          {
-            int lo = 0, hi = G::NCELL - 1;  // first c with cs[c + 1] > p0
-            while (lo < hi) { const int m = (lo + hi) >> 1; if (cs[m + 1] > p0) hi = m; else lo = m + 1; }
-            ca = lo;
-            lo = ca; hi = G::NCELL - 1;     // first c with cs[c + 1] >= p1
-            while (lo < hi) { const int m = (lo + hi) >> 1; if (cs[m + 1] >= p1) hi = m; else lo = m + 1; }
-            cb = lo;
-          }
-          const int ncp = cb - ca + 1;
-          int parts = 1;
-          while (parts * 2 * ncp <= NTHREADS && parts < 32) parts *= 2;
-          if (tid < ncp * parts) {
-            const int c = ca + tid % ncp, part = tid / ncp;
-            const int ia = max(cs[c], p0) + part, ib = min(cs[c + 1], p1);
-            if (ia < ib) {
-              T acc[P::NACC];
+        if constexpr (P::FAST) {
+          __syncwarp();
+          // -- 2. deposit the parked trajectories: one lane per (cell, part), stencil in registers
+          const int mya = max(cs[c_lo + lane], pa), myb = min(cs[c_lo + lane + 1], pb);
+          const unsigned cm = __ballot_sync(FULL, np > 0 && mya < myb);
+          if (cm) {
+            const int first = __ffs(cm) - 1;
+            const int ncp = 32 - __clz(cm) - first;  // cells that overlap [pa, pb) are contiguous
+            int parts = 1;
+            while (parts * 2 * ncp <= 32) parts *= 2;
+            const bool on = lane < ncp * parts;
+            const int cl = first + lane % ncp, part = lane / ncp;
+            const int c = c_lo + cl;
+            const int ia = on ? max(cs[c], pa) + part : 0, ib = on ? min(cs[c + 1], pb) : 0;
+            T acc[P::NACC];
 #pragma unroll
-              for (int k = 0; k < P::NACC; k++) acc[k] = T(0);
-              for (int i = ia; i < ib; i += parts) {
-                const int j = i - p0;
-                Seg<DIM, T> sg;
+            for (int k = 0; k < P::NACC; k++) acc[k] = T(0);
+            for (int i = ia; i < ib; i += parts) {
+              const int j = i - pa;
+              Seg<DIM, T> sg;
 #pragma unroll
-                for (int d = 0; d < DIM; d++) {
-                  sg.p0[d] = buf[d * np + j];
-                  sg.p1[d] = buf[(DIM + d) * np + j];
-                }
-                const T q = buf[2 * DIM * np + j];
-                if (DIM == 2) sg.vz = buf[(2 * DIM + 1) * np + j];
-                segment_current<DIM, ORDER, T>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
-                  T &r = acc[P::acc_index(comp, k1, k2, k3)];
-                  r = fmadd(f1, f2, r);
-                });
+              for (int d = 0; d < DIM; d++) {
+                sg.p0[d] = wbuf[d * np + j];
+                sg.p1[d] = wbuf[(DIM + d) * np + j];
               }
-              int lc[3];
-              lc[0] = c % G::TX;
-              lc[1] = (c / G::TX) % G::TY;
-              lc[2] = c / (G::TX * G::TY);
-              T *pj = jt + jtile_base<DIM, ORDER, T>(lc);
+              const T q = wbuf[2 * DIM * np + j];
+              if (DIM == 2) sg.vz = wbuf[(2 * DIM + 1) * np + j];
+              segment_current<DIM, ORDER, T>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
+                T &r = acc[P::acc_index(comp, k1, k2, k3)];
+                r = fmadd(f1, f2, r);
+              });
+            }
+            int lc[3];
+            lc[0] = c % G::TX;
+            lc[1] = (c / G::TX) % G::TY;
+            lc[2] = c / (G::TX * G::TY);
+            T *pj = jt + jtile_base<DIM, ORDER, T>(lc);
+            if (ncp == 32) {
+              // lanes are consecutive cells along x: neighbours add up the stencil columns they
+              // share with warp shuffles; one shared atomic per grid point of the row instead of
+              // one per cell and point
+              flush_merged<DIM, ORDER, T, P>(acc, pj, lc[0]);
+            } else if (ia < ib) {
               for_each_stencil_entry<DIM, ORDER>([&](int comp, int k1, int k2, int k3) {
                 atomicAdd(pj + comp * G::JVOL + k1 + G::JX * (k2 + G::JY * k3),
                           acc[P::acc_index(comp, k1, k2, k3)]);
               });
             }
           }
-          // -- 3. listed neighbour-cell pieces, one thread per piece -----------------------------
-          const int nx = min(s_nx[piece & 1], xcap);
-          if (tid == 0) s_nx[(piece + 1) & 1] = 0;
-          for (int e = tid; e < nx; e += NTHREADS) {
+          // -- 3. listed pieces, one lane per piece -------------------------------------------------
+          const int nxl = min(nxw, xcap);
+          for (int e = lane; e < nxl; e += 32) {
             Seg<DIM, T> sg;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
@@ -365,11 +439,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             for (int d = 0; d < DIM; d++) sg.c[d] = ((pc >> (5 * d)) & 31) - 1;
             deposit_segment<DIM, ORDER, T>(sg, q, jt, a.k, atomic_add);
           }
-          __syncthreads();  // the next piece reuses buf
+          __syncwarp();  // the next piece reuses the warp's buffer
         }
-      }
-      p0 = p1;
-      piece++;
+        pa = pb;
+      } while (pa < sb);
     }
     __syncthreads();  // J tile, histogram and scratch complete
 

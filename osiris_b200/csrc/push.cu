@@ -77,6 +77,21 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, const void *src, int c0, int c1,
+                                                  int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // exclusive block scan of one non-negative value per thread; *total = sum
 __device__ __forceinline__ int block_scan(int v, int *total, int *s_warp) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -110,7 +125,7 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr int DW = (DIM == 2) ? 6 : 7;  // parked trajectory: x0[D], x1[D], q, (vz)
   static constexpr int XW = DW + 1;              // listed piece: + packed tile-local cell
   // one private buffer per warp: parked trajectories from the bottom, the list above them
-  static constexpr int BUF_BYTES = FAST ? 76800 : 0;
+  static constexpr int BUF_BYTES = FAST ? 74752 : 0;
   static constexpr int WARP_WORDS = BUF_BYTES / (int)sizeof(T) / (NTHREADS / 32);
   static constexpr int XMIN = 40;  // list entries always available
   static constexpr int PCAP = FAST ? (((WARP_WORDS - XMIN * XW) / DW) & ~31) : 32;
@@ -118,7 +133,10 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
   static constexpr int OFF_BUF = OFF_JT + round_up(3 * G::JVOL * (int)sizeof(T), 16);
   static constexpr int OFF_CS = OFF_BUF + BUF_BYTES;
-  static constexpr int OFF_HIST = OFF_CS + round_up((G::NCELL + 1) * 4, 16);
+  static constexpr int CS_STRIDE = round_up(G::NCELL + 1, 4);
+  static constexpr int OFF_HIST = OFF_CS + 2 * CS_STRIDE * 4;
+  // J tile -> HBM with one TMA tensor reduce-add per component (fp32)
+  static constexpr bool TMA_J = sizeof(T) == 4;
   static constexpr int SMEM_BYTES = OFF_HIST + G::NCELL * 4;
   PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {
     return ((comp * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
@@ -187,10 +205,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   T *eb = reinterpret_cast<T *>(smem_raw);
   T *jt = reinterpret_cast<T *>(smem_raw + P::OFF_JT);
   T *buf = reinterpret_cast<T *>(smem_raw + P::OFF_BUF);
-  int *cs = reinterpret_cast<int *>(smem_raw + P::OFF_CS);
+  int *cs2 = reinterpret_cast<int *>(smem_raw + P::OFF_CS);  // two arrays: current / next tile
   int *hist = reinterpret_cast<int *>(smem_raw + P::OFF_HIST);
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ int s_tile, s_mcnt, s_base;
+  __shared__ int s_tile, s_n, s_ns, s_mcnt, s_base;
+  __shared__ long long s_off, s_next_off;
+  __shared__ int s_next[3];
   __shared__ int s_warp[NTHREADS / 32];
   __shared__ double s_ene[NTHREADS / 32];
 
@@ -200,61 +220,103 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   // this CTA's scratch range (new particle states in the old order, until the sort)
   const long long so = (long long)blockIdx.x * a.scr_stride;
 
+  // Tile bookkeeping is pipelined: while a tile is pushed, one thread has already taken the CTA's
+  // next tile from the device counter and asked L2 for its particle columns; as soon as the push
+  // is over (E/B tile free) the same thread starts the next tile's TMA loads, which then overlap
+  // the J write-back and the sort of the current tile.
+  auto take_tile = [&](int *n_out, int *ns_out, long long *off_out) {  // skips empty tiles
+    int t;
+    for (;;) {
+      t = atomicAdd(a.tile_counter, 1);
+      if (t >= a.tl.ntile) { *n_out = 0; return t; }
+      const int n = a.tile_cnt[t];
+      if (n > 0) {
+        *n_out = n;
+        *ns_out = P::FAST ? min(a.tile_nsorted[t], n) : 0;
+        *off_out = a.tile_off[t];
+        return t;
+      }
+      a.tile_nsorted[t] = 0;
+    }
+  };
+  auto tile_origin = [&](int tile, int *o0) {
+    int t = tile;
+    const int t0 = t % a.tl.nt[0]; t /= a.tl.nt[0];
+    const int t1 = t % a.tl.nt[1]; t /= a.tl.nt[1];
+    o0[0] = t0 * a.tl.T[0];
+    o0[1] = t1 * a.tl.T[1];
+    o0[2] = t * a.tl.T[2];
+  };
+  auto stage_fields = [&](int tile) {  // one thread: six TMA box loads of the tile's E/B + halo
+    int o0[3];
+    tile_origin(tile, o0);
+    mbar_expect_tx(&mbar, 6u * (uint32_t)(G::EVOL * sizeof(T)));
+    const int c0 = o0[0] + a.g.gl[0] + G::HALO_LO;
+    const int c1 = o0[1] + a.g.gl[1] + G::HALO_LO;
+    const int c2 = o0[2] + a.g.gl[2] + G::HALO_LO;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      if (DIM == 2) tma_load_2d(eb + c * G::ESTRIDE, &maps.m[c], &mbar, c0, c1);
+      else tma_load_3d(eb + c * G::ESTRIDE, &maps.m[c], &mbar, c0, c1, c2);
+    }
+  };
+  auto prefetch_particles = [&](int n, long long off) {  // one thread: ask L2 for a tile's columns
+    const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(T) + 15) & ~(size_t)15);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) l2_prefetch(a.sp.x[d] + off, bytes);
+#pragma unroll
+    for (int d = 0; d < 3; d++) l2_prefetch(a.sp.p[d] + off, bytes);
+    l2_prefetch(a.sp.q + off, bytes);
+    l2_prefetch(a.sp.cell + off, (uint32_t)(((size_t)n * 4 + 15) & ~(size_t)15));
+    l2_prefetch(a.sp.tag + off, (uint32_t)(((size_t)n * 8 + 15) & ~(size_t)15));
+  };
+
   if (tid == 0) {
     mbar_init(&mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_mcnt = 0;
+  }
+  for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
+  hist[tid] = 0;
+  __syncthreads();
+  if (tid == 32) {
+    int n = 0, ns = 0;
+    long long off = 0;
+    const int t = take_tile(&n, &ns, &off);
+    s_tile = t; s_n = n; s_ns = ns; s_off = off;
+    if (t < a.tl.ntile) stage_fields(t);
   }
   uint32_t phase = 0;
   double ene = 0.0;
+  int cur = 0;  // which of the two cell-offset arrays holds the current tile's
+  __syncthreads();
+  if (P::FAST && s_tile < a.tl.ntile && s_ns > 0) {
+    const int *g_cs = a.cell_start + (size_t)s_tile * (G::NCELL + 1);
+    cs2[tid] = g_cs[tid];
+    if (tid == 0) cs2[G::NCELL] = g_cs[G::NCELL];
+  }
 
   for (;;) {
-    __syncthreads();  // previous tile done with shared memory; mbarrier initialised
-    if (tid == 0) s_tile = atomicAdd(a.tile_counter, 1);
-    __syncthreads();
+    __syncthreads();  // s_tile .. s_off of this tile published
     const int tile = s_tile;
     if (tile >= a.tl.ntile) break;
-    const int n = a.tile_cnt[tile];
-    if (n == 0) {
-      if (tid == 0) a.tile_nsorted[tile] = 0;
-      continue;
-    }
-    const int ns = P::FAST ? min(a.tile_nsorted[tile], n) : 0;
-    const long long off = a.tile_off[tile];
+    const int n = s_n, ns = s_ns;
+    const long long off = s_off;
+    int *cs = cs2 + cur * P::CS_STRIDE;
 
     int o0[3], tlim[3];
-    {
-      int t = tile;
-      const int t0 = t % a.tl.nt[0]; t /= a.tl.nt[0];
-      const int t1 = t % a.tl.nt[1]; t /= a.tl.nt[1];
-      const int tc[3] = {t0, t1, t};
+    tile_origin(tile, o0);
 #pragma unroll
-      for (int d = 0; d < 3; d++) {
-        o0[d] = tc[d] * a.tl.T[d];
-        tlim[d] = min(a.tl.T[d], a.g.nx[d] - o0[d]);
-      }
-    }
+    for (int d = 0; d < 3; d++) tlim[d] = min(a.tl.T[d], a.g.nx[d] - o0[d]);
 
-    // ---- 0. stage E/B, clear J tile and histogram ------------------------------------------
-    if (tid == 0) {
-      s_mcnt = 0;
-      mbar_expect_tx(&mbar, 6u * (uint32_t)(G::EVOL * sizeof(T)));
-      const int c0 = o0[0] + a.g.gl[0] + G::HALO_LO;
-      const int c1 = o0[1] + a.g.gl[1] + G::HALO_LO;
-      const int c2 = o0[2] + a.g.gl[2] + G::HALO_LO;
-#pragma unroll
-      for (int c = 0; c < 6; c++) {
-        if (DIM == 2) tma_load_2d(eb + c * G::ESTRIDE, &maps.m[c], &mbar, c0, c1);
-        else tma_load_3d(eb + c * G::ESTRIDE, &maps.m[c], &mbar, c0, c1, c2);
-      }
+    // the CTA's next tile: taken now, its particle columns requested from L2, used at the end
+    if (tid == 32) {
+      int nx_n = 0, nx_ns = 0;
+      long long nx_off = 0;
+      const int nx_tile = take_tile(&nx_n, &nx_ns, &nx_off);
+      if (nx_tile < a.tl.ntile) prefetch_particles(nx_n, nx_off);
+      s_next[0] = nx_tile; s_next[1] = nx_n; s_next[2] = nx_ns; s_next_off = nx_off;
     }
-    for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
-    hist[tid] = 0;
-    if (P::FAST && ns > 0) {
-      const int *g_cs = a.cell_start + (size_t)tile * (G::NCELL + 1);
-      cs[tid] = g_cs[tid];
-      if (tid == 0) cs[G::NCELL] = g_cs[G::NCELL];
-    }
-    __syncthreads();
     mbar_wait(&mbar, phase);
     phase ^= 1;
 
@@ -444,31 +506,48 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         pa = pb;
       } while (pa < sb);
     }
-    __syncthreads();  // J tile, histogram and scratch complete
+    __syncthreads();  // J tile, histogram and scratch complete; E/B tile and cs free
 
-    // ---- 4. J tile -> HBM -------------------------------------------------------------------
-    for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) {
-      const T v = jt[i];
-      if (v != T(0)) {
-        const int c = i / G::JVOL;
-        int r = i - c * G::JVOL;
-        const int kx = r % G::JX; r /= G::JX;
-        const int ky = r % G::JY;
-        const int kz = r / G::JY;
-        const int q0 = o0[0] + a.g.gl[0] + G::HALO_LO + kx;
-        const int q1 = o0[1] + a.g.gl[1] + G::HALO_LO + ky;
-        const int q2 = (DIM == 3) ? o0[2] + a.g.gl[2] + G::HALO_LO + kz : 0;
-        if (q0 >= 0 && q0 < a.g.S[0] && q1 >= 0 && q1 < a.g.S[1] && q2 >= 0 && q2 < a.g.S[2])
-          atomicAdd(&a.J[c][a.g.at(q0, q1, q2)], v);
-        else
-          atomicOr(a.errflag, ERRF_BAD_CELL);
+    // ---- 4. J tile -> HBM; the next tile's E/B loads start ----------------------------------
+    if constexpr (P::TMA_J) {
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // atomics -> visible to TMA
+        const int c0 = o0[0] + a.g.gl[0] + G::HALO_LO;
+        const int c1 = o0[1] + a.g.gl[1] + G::HALO_LO;
+        const int c2 = o0[2] + a.g.gl[2] + G::HALO_LO;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (DIM == 2) tma_reduce_add_2d(&maps.m[6 + c], jt + c * G::JVOL, c0, c1);
+          else tma_reduce_add_3d(&maps.m[6 + c], jt + c * G::JVOL, c0, c1, c2);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+    } else {
+      for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) {
+        const T v = jt[i];
+        if (v != T(0)) {
+          const int c = i / G::JVOL;
+          int r = i - c * G::JVOL;
+          const int kx = r % G::JX; r /= G::JX;
+          const int ky = r % G::JY;
+          const int kz = r / G::JY;
+          const int q0 = o0[0] + a.g.gl[0] + G::HALO_LO + kx;
+          const int q1 = o0[1] + a.g.gl[1] + G::HALO_LO + ky;
+          const int q2 = (DIM == 3) ? o0[2] + a.g.gl[2] + G::HALO_LO + kz : 0;
+          if (q0 >= 0 && q0 < a.g.S[0] && q1 >= 0 && q1 < a.g.S[1] && q2 >= 0 && q2 < a.g.S[2])
+            atomicAdd(&a.J[c][a.g.at(q0, q1, q2)], v);
+        }
+      }
+    }
+    if (tid == 32) {
+      s_tile = s_next[0]; s_n = s_next[1]; s_ns = s_next[2]; s_off = s_next_off;
+      if (s_next[0] < a.tl.ntile) stage_fields(s_next[0]);
     }
 
     // ---- 5. sort by new cell: scratch -> particle buffer, leavers -> movers -----------------
     int nlive;
     const int start = block_scan(hist[tid], &nlive, s_warp);
-    cs[tid] = start;
+    hist[tid] = start;  // counts -> offsets
     const int nmov = n - nlive;
     if (tid == 0) {
       int b = 0;
@@ -490,36 +569,91 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     }
     __syncthreads();
     const int base = s_base;
-    for (int i = tid; i < n; i += NTHREADS) {
-      const long long r = so + i;
-      const int cell = a.scr.cell[r];
-      if (cell < 0) {
-        if (base >= 0) {
-          const int m = base + atomicAdd(&s_mcnt, 1);
+    // cell offsets of the CTA's next tile (published by thread 32 above): loaded now, stored below
+    int pre = 0, pre_last = 0;
+    const bool pre_on = P::FAST && s_tile < a.tl.ntile && s_ns > 0;
+    if (pre_on) {
+      const int *g_cs = a.cell_start + (size_t)s_tile * (G::NCELL + 1);
+      pre = g_cs[tid];
+      if (tid == 0) pre_last = g_cs[G::NCELL];
+    }
+    // four particles per thread in flight: the scratch range sits in L2, latency is what costs
+    for (int i0 = 0; i0 < n; i0 += 4 * NTHREADS) {
+      int cellv[4], rk[4];
+      long long dst[4];
+      bool act[4];
 #pragma unroll
-          for (int d = 0; d < DIM; d++) {
-            a.mv.x[d][m] = a.scr.x[d][r];
-            a.mv.ix[d][m] = o0[d] + cell_l(cell & ~CELL_DEAD, d) + 1;
-          }
+      for (int k = 0; k < 4; k++) {
+        const int i = i0 + tid + k * NTHREADS;
+        act[k] = i < n;
+        cellv[k] = act[k] ? a.scr.cell[so + i] : 0;
+        rk[k] = act[k] ? a.scr_rank[so + i] : 0;
+      }
+      T vx[4][DIM], vp[4][3], vq[4];
+      long long vt[4];
 #pragma unroll
-          for (int d = 0; d < 3; d++) a.mv.p[d][m] = a.scr.p[d][r];
-          a.mv.q[m] = a.scr.q[r];
-          a.mv.tag[m] = a.scr.tag[r];
+      for (int k = 0; k < 4; k++) {
+        if (act[k]) {
+          const long long r = so + i0 + tid + k * NTHREADS;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) vx[k][d] = a.scr.x[d][r];
+#pragma unroll
+          for (int d = 0; d < 3; d++) vp[k][d] = a.scr.p[d][r];
+          vq[k] = a.scr.q[r];
+          vt[k] = a.scr.tag[r];
         }
-      } else {
-        int l[DIM];
+      }
 #pragma unroll
-        for (int d = 0; d < DIM; d++) l[d] = cell_l(cell, d);
-        const long long s = off + cs[linear_cell<DIM>(l)] + a.scr_rank[r];
+      for (int k = 0; k < 4; k++) {
+        dst[k] = -1;
+        if (act[k]) {
+          if (cellv[k] < 0) {
+            if (base >= 0) dst[k] = base + atomicAdd(&s_mcnt, 1);
+          } else {
+            int l[DIM];
 #pragma unroll
-        for (int d = 0; d < DIM; d++) a.sp.x[d][s] = a.scr.x[d][r];
+            for (int d = 0; d < DIM; d++) l[d] = cell_l(cellv[k], d);
+            dst[k] = off + hist[linear_cell<DIM>(l)] + rk[k];
+          }
+        }
+      }
 #pragma unroll
-        for (int d = 0; d < 3; d++) a.sp.p[d][s] = a.scr.p[d][r];
-        a.sp.q[s] = a.scr.q[r];
-        a.sp.cell[s] = cell;
-        a.sp.tag[s] = a.scr.tag[r];
+      for (int k = 0; k < 4; k++) {
+        if (dst[k] >= 0) {
+          const long long s = dst[k];
+          if (cellv[k] < 0) {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+              a.mv.x[d][s] = vx[k][d];
+              a.mv.ix[d][s] = o0[d] + cell_l(cellv[k] & ~CELL_DEAD, d) + 1;
+            }
+#pragma unroll
+            for (int d = 0; d < 3; d++) a.mv.p[d][s] = vp[k][d];
+            a.mv.q[s] = vq[k];
+            a.mv.tag[s] = vt[k];
+          } else {
+#pragma unroll
+            for (int d = 0; d < DIM; d++) a.sp.x[d][s] = vx[k][d];
+#pragma unroll
+            for (int d = 0; d < 3; d++) a.sp.p[d][s] = vp[k][d];
+            a.sp.q[s] = vq[k];
+            a.sp.cell[s] = cellv[k];
+            a.sp.tag[s] = vt[k];
+          }
+        }
       }
     }
+    if (pre_on) {
+      int *cs_next = cs2 + (cur ^ 1) * P::CS_STRIDE;
+      cs_next[tid] = pre;
+      if (tid == 0) cs_next[G::NCELL] = pre_last;
+    }
+    if (P::TMA_J && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();  // sort done (offsets in hist free), J tile read by the TMA
+    for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
+    hist[tid] = 0;
+    if (tid == 0) s_mcnt = 0;
+    cur ^= 1;
   }
 
   // ---- energy: warp shuffle, then one atomic per CTA ----------------------------------------
@@ -565,19 +699,20 @@ template int launch_push_deposit<float>(int, int, const TmaMaps &, const PushArg
 template int launch_push_deposit<double>(int, int, const TmaMaps &, const PushArgs<double> &, int,
                                          cudaStream_t);
 
-template <typename T> void push_tile_shape(int dim, int order, int *box, int *smem_bytes) {
+template <typename T> void push_tile_shape(int dim, int order, int *box, int *jbox, int *smem_bytes) {
 #define CASE(D, O)                                         \
   if (dim == D && order == O) {                            \
     using G = Tile<D, O, T>;                               \
     box[0] = G::EXP; box[1] = G::EY; box[2] = G::EZ;       \
+    jbox[0] = G::JX; jbox[1] = G::JY; jbox[2] = G::JZ;     \
     *smem_bytes = Plan<D, O, T>::SMEM_BYTES;               \
     return;                                                \
   }
   CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 1) CASE(3, 2) CASE(3, 3) CASE(3, 4)
 #undef CASE
 }
-template void push_tile_shape<float>(int, int, int *, int *);
-template void push_tile_shape<double>(int, int, int *, int *);
+template void push_tile_shape<float>(int, int, int *, int *, int *);
+template void push_tile_shape<double>(int, int, int *, int *, int *);
 
 // resident CTAs per SM of the instantiation (the persistent grid is nSM x this)
 template <typename T> int push_blocks_per_sm(int dim, int order) {

@@ -6,9 +6,10 @@
 
 namespace osgpu {
 
-// tensor maps of E1..3, B1..3 (one box = one tile + halo), passed as a __grid_constant__
+// tensor maps of E1..3, B1..3 (box = one tile + interpolation halo, loaded) and J1..3 (box = one
+// tile + deposit halo, reduce-added), passed as a __grid_constant__
 struct alignas(64) TmaMaps {
-  CUtensorMap m[6];
+  CUtensorMap m[9];
 };
 
 template <typename T> struct PushArgs {
@@ -36,6 +37,6 @@ int launch_push_deposit(int dim, int order, const TmaMaps &maps, const PushArgs<
 // resident CTAs per SM of the kernel for (dim, order)
 template <typename T> int push_blocks_per_sm(int dim, int order);
 // TMA box (elements, fastest first) and dynamic shared memory of the kernel for (dim, order)
-template <typename T> void push_tile_shape(int dim, int order, int *box, int *smem_bytes);
+template <typename T> void push_tile_shape(int dim, int order, int *box, int *jbox, int *smem_bytes);
 
 }  // namespace osgpu

@@ -222,14 +222,15 @@ template <typename T> struct Sim final : SimBase {
       set_error("cuTensorMapEncodeTiled not available from the driver");
       return OSGPU_ERR_CUDA;
     }
-    int box[3], smem;
-    push_tile_shape<T>(dim, order, box, &smem);
+    int box[3], jbox[3], smem;
+    push_tile_shape<T>(dim, order, box, jbox, &smem);
     const cuuint64_t gdim[3] = {(cuuint64_t)g.P0, (cuuint64_t)g.S[1], (cuuint64_t)g.S[2]};
     const cuuint64_t gstr[2] = {(cuuint64_t)g.P0 * sizeof(T), (cuuint64_t)g.P0 * g.S[1] * sizeof(T)};
-    const cuuint32_t bx[3] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)box[2]};
     const cuuint32_t es[3] = {1, 1, 1};
-    for (int c = 0; c < 6; c++) {
-      T *base = (c < 3) ? E.c[c] : B.c[c - 3];
+    for (int c = 0; c < 9; c++) {
+      T *base = (c < 3) ? E.c[c] : (c < 6 ? B.c[c - 3] : J.c[c - 6]);
+      const int *bb = (c < 6) ? box : jbox;
+      const cuuint32_t bx[3] = {(cuuint32_t)bb[0], (cuuint32_t)bb[1], (cuuint32_t)bb[2]};
       CUresult r = ((encode_fn)fn)(&maps.m[c],
                                    sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
                                    (cuuint32_t)dim, base, gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -27,8 +27,10 @@ template <int DIM, int ORDER, typename T> struct Tile {
   // per-component stride keeps every TMA destination 128-byte aligned
   static constexpr int ESTRIDE = round_up(EVOL * (int)sizeof(T), 128) / (int)sizeof(T);
   // J tile: deposit points of a segment in cell l + d, d in {-1,0,1}
-  static constexpr int JX = TX + NP + 1, JY = TY + NP + 1, JZ = (DIM == 3) ? TZ + NP + 1 : 1;
-  static constexpr int JVOL = JX * JY * JZ;
+  // (rows padded to 16 bytes, components to 128 bytes: the J tile leaves as TMA reduce boxes)
+  static constexpr int JX = round_up(TX + NP + 1, 16 / (int)sizeof(T));
+  static constexpr int JY = TY + NP + 1, JZ = (DIM == 3) ? TZ + NP + 1 : 1;
+  static constexpr int JVOL = round_up(JX * JY * JZ * (int)sizeof(T), 128) / (int)sizeof(T);
   // first E/B (and J) tile point, in cells relative to the tile's first cell
   static constexpr int HALO_LO = LP - 1;
   static constexpr int SMEM_BYTES = (6 * ESTRIDE + 3 * JVOL) * (int)sizeof(T);

@@ -137,7 +137,8 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr int OFF_HIST = OFF_CS + 2 * CS_STRIDE * 4;
   // J tile -> HBM with one TMA tensor reduce-add per component (fp32)
   static constexpr bool TMA_J = sizeof(T) == 4;
-  static constexpr int SMEM_BYTES = OFF_HIST + G::NCELL * 4;
+  static constexpr int OFF_HEADS = OFF_HIST + G::NCELL * 4;
+  static constexpr int SMEM_BYTES = OFF_HEADS + G::NCELL * 4;
   PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {
     return ((comp * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
   }
@@ -207,7 +208,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   T *buf = reinterpret_cast<T *>(smem_raw + P::OFF_BUF);
   int *cs2 = reinterpret_cast<int *>(smem_raw + P::OFF_CS);  // two arrays: current / next tile
   int *hist = reinterpret_cast<int *>(smem_raw + P::OFF_HIST);
+  int *heads = reinterpret_cast<int *>(smem_raw + P::OFF_HEADS);  // per cell: list of foreign pieces
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ int s_xl[NTHREADS / 32], s_xcap[NTHREADS / 32];
   __shared__ int s_tile, s_n, s_ns, s_mcnt, s_base;
   __shared__ long long s_off, s_next_off;
   __shared__ int s_next[3];
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   }
   for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
   hist[tid] = 0;
+  heads[tid] = 0;
   __syncthreads();
   if (tid == 32) {
     int n = 0, ns = 0;
@@ -320,7 +324,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     mbar_wait(&mbar, phase);
     phase ^= 1;
 
-    // ---- 1..3: every warp works through its own 32 cells without CTA-wide barriers --------
+    // ---- 1..3: push, then deposit; every trajectory piece inside the tile is routed to the lane
+    // that owns its cell, so its current is accumulated in registers ----------------------------
     {
       constexpr unsigned FULL = 0xffffffffu;
       const unsigned lt_mask = (1u << lane) - 1u;
@@ -332,13 +337,23 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       T *wbuf = buf + wid * P::WARP_WORDS;
 
       int pa = sa;
+      bool more, tail_taken = false;
       do {
         const int pb = min(sb, pa + P::PCAP);
         const int np = pb - pa;                       // parked trajectories of this piece
-        const int tot = np + ((pb == sb) ? tb - ta : 0);  // the last piece also takes the tail share
-        T *xl = wbuf + P::DW * np;                    // list of pieces to deposit one by one
-        const int xcap = (P::WARP_WORDS - P::DW * np) / P::XW;
-        int nxw = 0;                                  // warp-uniform list length
+        const bool take_tail = (pb == sb) && !tail_taken;  // the last piece also takes the tail share
+        tail_taken |= take_tail;
+        const int tot = np + (take_tail ? tb - ta : 0);
+        // list of pieces outside their particle's cell, above the parked trajectories: pieces in
+        // tile cells grow from the bottom (linked to their cell), halo pieces from the top
+        T *xl = wbuf + P::DW * np;
+        const int xcap = P::FAST ? (P::WARP_WORDS - P::DW * np) / P::XW : 0;
+        const int xcap_lo = xcap - xcap / 4;
+        int nlo = 0, nhi = 0;                         // warp-uniform list lengths
+        if (P::FAST && lane == 0) {
+          s_xl[wid] = (int)(xl - buf);
+          s_xcap[wid] = xcap;
+        }
 
         // -- 1. push, 32 particles per round; the next round's loads are issued first ----------
         T nx_[DIM], nu_[3], nq_ = T(0);
@@ -407,15 +422,24 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               if (DIM == 2) wbuf[(2 * DIM + 1) * np + m] = seg[0].vz;
             }
           }
-          // pieces in neighbouring cells (and every piece of a tail particle) go to the list
+          // pieces outside the particle's own cell (and every piece of a tail particle)
           unsigned direct = 0;
 #pragma unroll
           for (int k = 0; k <= DIM; k++) {
             const bool has = active && (k < nseg) && (k > 0 || !(P::FAST && parked));
-            const unsigned hm = __ballot_sync(FULL, has);
+            bool inside = true;
+            int lcell = 0;
             if (has) {
-              const int e = nxw + __popc(hm & lt_mask);
-              if (P::FAST && e < xcap) {
+#pragma unroll
+              for (int d = 0; d < DIM; d++) inside &= (seg[k].c[d] >= 0) && (seg[k].c[d] < (d == 0 ? G::TX : (d == 1 ? G::TY : G::TZ)));
+              lcell = linear_cell<DIM>(seg[k].c);
+            }
+            const unsigned hm = __ballot_sync(FULL, has);
+            const unsigned im = __ballot_sync(FULL, has && inside);
+            if (has) {
+              const int e = inside ? nlo + __popc(im & lt_mask) : xcap - 1 - (nhi + __popc((hm & ~im) & lt_mask));
+              const bool fits = P::FAST && (inside ? e < xcap_lo : e >= xcap_lo);
+              if (fits) {
 #pragma unroll
                 for (int d = 0; d < DIM; d++) {
                   xl[d * xcap + e] = seg[k].p0[d];
@@ -423,36 +447,50 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
                 }
                 xl[2 * DIM * xcap + e] = q;
                 if (DIM == 2) xl[(2 * DIM + 1) * xcap + e] = seg[k].vz;
-                int pc = 0;  // cell coordinates -1..T in 5-bit fields: exact as a float
+                int link;
+                if (inside) {
+                  link = atomicExch(&heads[lcell], ((wid << 12) | e) + 1);  // push on the cell's list
+                } else {
+                  link = 0;  // cell coordinates -1..T in 5-bit fields (exact as a float)
 #pragma unroll
-                for (int d = 0; d < DIM; d++) pc |= (seg[k].c[d] + 1) << (5 * d);
-                xl[P::DW * xcap + e] = (T)pc;
+                  for (int d = 0; d < DIM; d++) link |= (seg[k].c[d] + 1) << (5 * d);
+                }
+                xl[P::DW * xcap + e] = (T)link;
               } else {
                 direct |= 1u << k;
               }
             }
-            nxw += __popc(hm);
+            nlo += __popc(im);
+            nhi += __popc(hm & ~im);
           }
           if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
         }
 
+        more = __syncthreads_or(pb < sb);  // every warp's lists are complete
+
         if constexpr (P::FAST) {
-          __syncwarp();
-          // -- 2. deposit the parked trajectories: one lane per (cell, part), stencil in registers
+          // -- 2. deposit: one lane per (cell, part) walks the cell's parked trajectories and its
+          // list of foreign pieces; the whole stencil is accumulated in registers -------------
           const int mya = max(cs[c_lo + lane], pa), myb = min(cs[c_lo + lane + 1], pb);
-          const unsigned cm = __ballot_sync(FULL, np > 0 && mya < myb);
+          const unsigned cm = __ballot_sync(FULL, (np > 0 && mya < myb) || heads[c_lo + lane] != 0);
           if (cm) {
             const int first = __ffs(cm) - 1;
-            const int ncp = 32 - __clz(cm) - first;  // cells that overlap [pa, pb) are contiguous
+            const int ncp = 32 - __clz(cm) - first;
             int parts = 1;
             while (parts * 2 * ncp <= 32) parts *= 2;
             const bool on = lane < ncp * parts;
             const int cl = first + lane % ncp, part = lane / ncp;
             const int c = c_lo + cl;
-            const int ia = on ? max(cs[c], pa) + part : 0, ib = on ? min(cs[c + 1], pb) : 0;
+            const int ia = (on && np > 0) ? max(cs[c], pa) + part : 0, ib = (on && np > 0) ? min(cs[c + 1], pb) : 0;
             T acc[P::NACC];
 #pragma unroll
             for (int k = 0; k < P::NACC; k++) acc[k] = T(0);
+            const auto accumulate = [&](const Seg<DIM, T> &sg, T q) {
+              segment_current<DIM, ORDER, T>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
+                T &r = acc[P::acc_index(comp, k1, k2, k3)];
+                r = fmadd(f1, f2, r);
+              });
+            };
             for (int i = ia; i < ib; i += parts) {
               const int j = i - pa;
               Seg<DIM, T> sg;
@@ -463,10 +501,26 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               }
               const T q = wbuf[2 * DIM * np + j];
               if (DIM == 2) sg.vz = wbuf[(2 * DIM + 1) * np + j];
-              segment_current<DIM, ORDER, T>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
-                T &r = acc[P::acc_index(comp, k1, k2, k3)];
-                r = fmadd(f1, f2, r);
-              });
+              accumulate(sg, q);
+            }
+            int id = (on && part == 0) ? heads[c] : 0;
+            if (on && part == 0 && id) heads[c] = 0;
+            bool any = ia < ib;
+            while (id) {
+              any = true;
+              const int w = (id - 1) >> 12, e = (id - 1) & 4095;
+              const T *xe = buf + s_xl[w] + e;
+              const int st = s_xcap[w];
+              Seg<DIM, T> sg;
+#pragma unroll
+              for (int d = 0; d < DIM; d++) {
+                sg.p0[d] = xe[d * st];
+                sg.p1[d] = xe[(DIM + d) * st];
+              }
+              const T q = xe[2 * DIM * st];
+              if (DIM == 2) sg.vz = xe[(2 * DIM + 1) * st];
+              id = (int)xe[P::DW * st];
+              accumulate(sg, q);
             }
             int lc[3];
             lc[0] = c % G::TX;
@@ -478,16 +532,15 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               // share with warp shuffles; one shared atomic per grid point of the row instead of
               // one per cell and point
               flush_merged<DIM, ORDER, T, P>(acc, pj, lc[0]);
-            } else if (ia < ib) {
+            } else if (any) {
               for_each_stencil_entry<DIM, ORDER>([&](int comp, int k1, int k2, int k3) {
                 atomicAdd(pj + comp * G::JVOL + k1 + G::JX * (k2 + G::JY * k3),
                           acc[P::acc_index(comp, k1, k2, k3)]);
               });
             }
           }
-          // -- 3. listed pieces, one lane per piece -------------------------------------------------
-          const int nxl = min(nxw, xcap);
-          for (int e = lane; e < nxl; e += 32) {
+          // -- 3. pieces in halo cells (owned by a neighbouring tile): straight into the J tile --
+          for (int e = xcap - 1 - lane; e >= max(xcap - nhi, xcap_lo); e -= 32) {
             Seg<DIM, T> sg;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
@@ -501,10 +554,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             for (int d = 0; d < DIM; d++) sg.c[d] = ((pc >> (5 * d)) & 31) - 1;
             deposit_segment<DIM, ORDER, T>(sg, q, jt, a.k, atomic_add);
           }
-          __syncwarp();  // the next piece reuses the warp's buffer
         }
+        if (more) __syncthreads();  // the next piece reuses the buffers other warps may still read
         pa = pb;
-      } while (pa < sb);
+      } while (more);
     }
     __syncthreads();  // J tile, histogram and scratch complete; E/B tile and cs free
 

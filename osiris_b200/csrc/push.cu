@@ -47,6 +47,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -128,7 +131,7 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr int BUF_BYTES = FAST ? 74752 : 0;
   static constexpr int WARP_WORDS = BUF_BYTES / (int)sizeof(T) / (NTHREADS / 32);
   static constexpr int XMIN = 40;  // list entries always available
-  static constexpr int PCAP = FAST ? (((WARP_WORDS - XMIN * XW) / DW) & ~31) : 32;
+  static constexpr int PCAP = FAST ? (((WARP_WORDS - XMIN * XW) / DW) & ~31) : (1 << 30);
   static constexpr int NACC = 3 * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
   static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
   static constexpr int OFF_BUF = OFF_JT + round_up(3 * G::JVOL * (int)sizeof(T), 16);
@@ -150,30 +153,58 @@ template <int DIM> __device__ __forceinline__ int linear_cell(const int *l) {
   else return l[0] + G::TX * (l[1] + G::TY * l[DIM - 1]);
 }
 
+// N independent shared-memory adds with two round trips instead of N serialised compare-and-swap
+// loops (fp32/fp64 atomicAdd on shared memory is an ATOMS.CAST.SPIN loop on sm_100a): read all the
+// old values, then try every update with one CAS each; an update that lost a race falls back to
+// the ordinary atomicAdd.  The addresses of one batch must not alias inside the warp.
+__device__ __forceinline__ bool cas_add(float *p, float old, float v) {
+  const int o = __float_as_int(old);
+  return atomicCAS(reinterpret_cast<int *>(p), o, __float_as_int(old + v)) == o;
+}
+__device__ __forceinline__ bool cas_add(double *p, double old, double v) {
+  const unsigned long long o = (unsigned long long)__double_as_longlong(old);
+  return atomicCAS(reinterpret_cast<unsigned long long *>(p), o,
+                   (unsigned long long)__double_as_longlong(old + v)) == o;
+}
+template <typename T, int N> __device__ __forceinline__ void add_batch(T *const (&p)[N], const T (&v)[N]) {
+  T old[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) old[k] = *reinterpret_cast<volatile T *>(p[k]);
+#pragma unroll
+  for (int k = 0; k < N; k++)
+    if (!cas_add(p[k], old[k], v[k])) atomicAdd(p[k], v[k]);
+}
+
 // Flush of the per-cell stencil accumulators when the 32 lanes of a warp hold 32 consecutive cells
 // (rows of TX cells along x).  The stencils of x-neighbours overlap: the lane that owns a grid
 // column (the one whose entry k1 = KO lands there) collects its neighbours' entries for that
-// column with shuffles and issues the only shared-memory atomic; entries whose owner would lie
-// outside the row are added by the lane itself.
+// column with shuffles and issues the only shared-memory update; entries whose owner would lie
+// outside the row are added by the lane itself.  Updates are issued in batches of one y-row of
+// the stencil (k2 fixed): inside a batch no two lanes of the warp touch the same word.
 template <int DIM, int ORDER, typename T, class P>
 __device__ __forceinline__ void flush_merged(const T *acc, T *pj, int x) {
   using G = Tile<DIM, ORDER, T>;
   constexpr int NP = G::NP;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int NZ = (DIM == 3) ? NP : 1;
+  // entries along x and the owner entry, per component
+  constexpr int NK1[3] = {NP - 1, NP, NP};
+  constexpr int KO[3] = {(NP - 2 < 1) ? NP - 2 : 1, (NP - 1 < 1) ? NP - 1 : 1, (NP - 1 < 1) ? NP - 1 : 1};
 #pragma unroll
-  for (int comp = 0; comp < 3; comp++) {
-    constexpr int dummy = 0;
-    (void)dummy;
+  for (int k2 = 0; k2 < NP; k2++) {
+    // -- columns owned by this lane --
+    constexpr int NZ2 = (DIM == 3) ? NZ - 1 : NZ;  // component-3 entries per row
+    constexpr int NB = 2 * NZ + NZ2;               // entries of a row (the last row has no component 2)
+    T *bp[NB];
+    T bv[NB];
+    int nb = 0;
 #pragma unroll
-    for (int k3 = 0; k3 < NZ; k3++) {
+    for (int comp = 0; comp < 3; comp++) {
+      if (comp == 1 && k2 >= NP - 1) continue;
 #pragma unroll
-      for (int k2 = 0; k2 < NP; k2++) {
-        if (comp == 1 && k2 >= NP - 1) continue;
+      for (int k3 = 0; k3 < NZ; k3++) {
         if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
-        const int nk1 = (comp == 0) ? NP - 1 : NP;  // entries along x
-        const int ko = (nk1 - 1 < 1) ? nk1 - 1 : 1; // owner entry
-        T *row = pj + comp * G::JVOL + G::JX * (k2 + G::JY * k3);
+        const int nk1 = NK1[comp], ko = KO[comp];
         T m = acc[P::acc_index(comp, ko, k2, k3)];
 #pragma unroll
         for (int d = 1; d <= ko; d++) {  // entry ko - d of the lane d cells to the right
@@ -185,12 +216,36 @@ __device__ __forceinline__ void flush_merged(const T *acc, T *pj, int x) {
           const T t = __shfl_up_sync(FULL, acc[P::acc_index(comp, ko + d, k2, k3)], d);
           if (x - d >= 0) m += t;
         }
-        atomicAdd(row + ko, m);
+        bp[nb] = pj + comp * G::JVOL + G::JX * (k2 + G::JY * k3) + ko;
+        bv[nb] = m;
+        nb++;
+      }
+    }
+    if (k2 < NP - 1) add_batch<T, NB>(bp, bv);
+    else {  // the last row has no component-1 entries
+      T *cp[NB - NZ];
+      T cv[NB - NZ];
 #pragma unroll
-        for (int k1 = 0; k1 < nk1; k1++) {
-          if (k1 == ko) continue;
-          const int xo = x + k1 - ko;  // owner cell of this column
-          if (xo < 0 || xo >= G::TX) atomicAdd(row + k1, acc[P::acc_index(comp, k1, k2, k3)]);
+      for (int k = 0; k < NB - NZ; k++) { cp[k] = bp[k]; cv[k] = bv[k]; }
+      add_batch<T, NB - NZ>(cp, cv);
+      static_assert(NB - NZ == NZ + NZ2, "row without component-2 entries");
+    }
+    // -- columns whose owner cell lies outside the row: first and last lane of the row --
+    if (x == 0 || x == G::TX - 1) {
+#pragma unroll
+      for (int comp = 0; comp < 3; comp++) {
+        if (comp == 1 && k2 >= NP - 1) continue;
+#pragma unroll
+        for (int k3 = 0; k3 < NZ; k3++) {
+          if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
+          const int nk1 = NK1[comp], ko = KO[comp];
+#pragma unroll
+          for (int k1 = 0; k1 < nk1; k1++) {
+            if (k1 == ko) continue;
+            const int xo = x + k1 - ko;  // owner cell of this column
+            if (xo < 0 || xo >= G::TX)
+              atomicAdd(pj + comp * G::JVOL + G::JX * (k2 + G::JY * k3) + k1, acc[P::acc_index(comp, k1, k2, k3)]);
+          }
         }
       }
     }
@@ -336,18 +391,20 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       const int ta = min(n, ns + wid * tchunk), tb = min(n, ta + tchunk);
       T *wbuf = buf + wid * P::WARP_WORDS;
 
-      int pa = sa;
-      bool more, tail_taken = false;
+      // the warp's work list: its sorted particles, then its tail share, in pieces of <= PCAP
+      const int nsw = sb - sa, totw = nsw + (tb - ta);
+      int qa = 0, it = 0;
+      bool more = false;
       do {
-        const int pb = min(sb, pa + P::PCAP);
-        const int np = pb - pa;                       // parked trajectories of this piece
-        const bool take_tail = (pb == sb) && !tail_taken;  // the last piece also takes the tail share
-        tail_taken |= take_tail;
-        const int tot = np + (take_tail ? tb - ta : 0);
+        const int qb = min(totw, qa + P::PCAP);
+        const int tot = qb - qa;                          // particles of this piece
+        const int np = max(0, min(qb, nsw) - qa);         // of which sorted: their trajectories are parked
+        const int pa = sa + qa, pb = pa + np;             // sorted particles [pa, pb)
+        const int tp = ta + max(0, qa - nsw) - np;        // tail particle of item m >= np: tp + m
         // list of pieces outside their particle's cell, above the parked trajectories: pieces in
         // tile cells grow from the bottom (linked to their cell), halo pieces from the top
-        T *xl = wbuf + P::DW * np;
-        const int xcap = P::FAST ? (P::WARP_WORDS - P::DW * np) / P::XW : 0;
+        T *xl = wbuf + P::DW * tot;
+        const int xcap = P::FAST ? (P::WARP_WORDS - P::DW * tot) / P::XW : 0;
         const int xcap_lo = xcap - xcap / 4;
         int nlo = 0, nhi = 0;                         // warp-uniform list lengths
         if (P::FAST && lane == 0) {
@@ -361,7 +418,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         long long ntag_ = 0;
         auto fetch = [&](int m) {
           if (m < tot) {
-            const long long s = off + ((m < np) ? pa + m : ta + (m - np));
+            const long long s = off + ((m < np) ? pa + m : tp + m);
 #pragma unroll
             for (int d = 0; d < DIM; d++) nx_[d] = a.sp.x[d][s];
 #pragma unroll
@@ -403,7 +460,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             int rank = 0;
             if (moved) ncell |= CELL_DEAD;
             else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
-            const long long r = so + ((m < np) ? pa + m : ta + (m - np));
+            const long long r = so + ((m < np) ? pa + m : tp + m);
 #pragma unroll
             for (int d = 0; d < DIM; d++) a.scr.x[d][r] = x[d];
 #pragma unroll
@@ -415,11 +472,11 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             if (P::FAST && parked) {
 #pragma unroll
               for (int d = 0; d < DIM; d++) {
-                wbuf[d * np + m] = seg[0].p0[d];
-                wbuf[(DIM + d) * np + m] = seg[0].p1[d];
+                wbuf[d * tot + m] = seg[0].p0[d];
+                wbuf[(DIM + d) * tot + m] = seg[0].p1[d];
               }
-              wbuf[2 * DIM * np + m] = q;
-              if (DIM == 2) wbuf[(2 * DIM + 1) * np + m] = seg[0].vz;
+              wbuf[2 * DIM * tot + m] = q;
+              if (DIM == 2) wbuf[(2 * DIM + 1) * tot + m] = seg[0].vz;
             }
           }
           // pieces outside the particle's own cell (and every piece of a tail particle)
@@ -466,7 +523,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
         }
 
-        more = __syncthreads_or(pb < sb);  // every warp's lists are complete
+        more = __syncthreads_or(qb < totw);  // every warp's lists are complete
 
         if constexpr (P::FAST) {
           // -- 2. deposit: one lane per (cell, part) walks the cell's parked trajectories and its
@@ -496,11 +553,11 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               Seg<DIM, T> sg;
 #pragma unroll
               for (int d = 0; d < DIM; d++) {
-                sg.p0[d] = wbuf[d * np + j];
-                sg.p1[d] = wbuf[(DIM + d) * np + j];
+                sg.p0[d] = wbuf[d * tot + j];
+                sg.p1[d] = wbuf[(DIM + d) * tot + j];
               }
-              const T q = wbuf[2 * DIM * np + j];
-              if (DIM == 2) sg.vz = wbuf[(2 * DIM + 1) * np + j];
+              const T q = wbuf[2 * DIM * tot + j];
+              if (DIM == 2) sg.vz = wbuf[(2 * DIM + 1) * tot + j];
               accumulate(sg, q);
             }
             int id = (on && part == 0) ? heads[c] : 0;
@@ -556,7 +613,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           }
         }
         if (more) __syncthreads();  // the next piece reuses the buffers other warps may still read
-        pa = pb;
+        qa = qb;
+        it++;
       } while (more);
     }
     __syncthreads();  // J tile, histogram and scratch complete; E/B tile and cs free

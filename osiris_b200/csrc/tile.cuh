@@ -178,22 +178,26 @@ PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Ou
     }
   } else {
     constexpr int Z = DIM - 1;  // == 2; written this way so the 2D instantiation compiles
-    // wp?[kb][ka] as in the reference: wp1[kz][ky], wp2[kz][kx], wp3[ky][kx]
+    // wp?[kb][ka] as in the reference (wp1[kz][ky], wp2[kz][kx], wp3[ky][kx]):
+    //   wp = S0a S0b + S1a S1b + (S0a S1b + S1a S0b) / 2 = S0a (S0b + S1b / 2) + S1a (S1b + S0b / 2)
+    // the transverse factors in brackets are formed once per axis (same value up to rounding;
+    // J is compared to the reference at 1e-5 max|J|, the summation order differs anyway)
+    T hz0[NP], hz1[NP], hy0[NP], hy1[NP];
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+      hz0[k] = fmadd(T(0.5), s1[Z][k], s0[Z][k]);
+      hz1[k] = fmadd(T(0.5), s0[Z][k], s1[Z][k]);
+      hy0[k] = fmadd(T(0.5), s1[1][k], s0[1][k]);
+      hy1[k] = fmadd(T(0.5), s0[1][k], s1[1][k]);
+    }
     T wp1[NP][NP], wp2[NP][NP], wp3[NP][NP];
 #pragma unroll
     for (int k2 = 0; k2 < NP; k2++)
 #pragma unroll
       for (int k1 = 0; k1 < NP; k1++) {
-        T t1, t2;
-        t1 = s0[1][k1] * s0[Z][k2]; t2 = s0[1][k1] * s1[Z][k2];
-        t1 = fmadd(s1[1][k1], s1[Z][k2], t1); t2 = fmadd(s1[1][k1], s0[Z][k2], t2);
-        wp1[k2][k1] = fmadd(T(0.5), t2, t1);
-        t1 = s0[0][k1] * s0[Z][k2]; t2 = s0[0][k1] * s1[Z][k2];
-        t1 = fmadd(s1[0][k1], s1[Z][k2], t1); t2 = fmadd(s1[0][k1], s0[Z][k2], t2);
-        wp2[k2][k1] = fmadd(T(0.5), t2, t1);
-        t1 = s0[0][k1] * s0[1][k2]; t2 = s0[0][k1] * s1[1][k2];
-        t1 = fmadd(s1[0][k1], s1[1][k2], t1); t2 = fmadd(s1[0][k1], s0[1][k2], t2);
-        wp3[k2][k1] = fmadd(T(0.5), t2, t1);
+        wp1[k2][k1] = fmadd(s1[1][k1], hz1[k2], s0[1][k1] * hz0[k2]);
+        wp2[k2][k1] = fmadd(s1[0][k1], hz1[k2], s0[0][k1] * hz0[k2]);
+        wp3[k2][k1] = fmadd(s1[0][k1], hy1[k2], s0[0][k1] * hy0[k2]);
       }
 #pragma unroll
     for (int k3 = 0; k3 < NP; k3++)

@@ -127,11 +127,12 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr bool FAST = ORDER <= 2;
   static constexpr int DW = (DIM == 2) ? 6 : 7;  // parked trajectory: x0[D], x1[D], q, (vz)
   static constexpr int XW = DW + 1;              // listed piece: + packed tile-local cell
-  // one private buffer per warp: parked trajectories from the bottom, the list above them
+  // one buffer per CTA: the parked trajectories of a piece from the bottom, above them one list
+  // region per warp
   static constexpr int BUF_BYTES = FAST ? 74752 : 0;
-  static constexpr int WARP_WORDS = BUF_BYTES / (int)sizeof(T) / (NTHREADS / 32);
-  static constexpr int XMIN = 40;  // list entries always available
-  static constexpr int PCAP = FAST ? (((WARP_WORDS - XMIN * XW) / DW) & ~31) : (1 << 30);
+  static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
+  static constexpr int XMIN = 40 * (NTHREADS / 32);  // list entries always available
+  static constexpr int TCAP = FAST ? (((BUF_WORDS - XMIN * XW) / DW) & ~255) : (1 << 30);
   static constexpr int NACC = 3 * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
   static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
   static constexpr int OFF_BUF = OFF_JT + round_up(3 * G::JVOL * (int)sizeof(T), 16);
@@ -385,26 +386,22 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       constexpr unsigned FULL = 0xffffffffu;
       const unsigned lt_mask = (1u << lane) - 1u;
       const int c_lo = 32 * wid;
-      // sorted particles of this warp's cells, and its share of the unsorted tail
-      const int sa = (ns > 0) ? cs[c_lo] : 0, sb = (ns > 0) ? cs[c_lo + 32] : 0;
-      const int tchunk = (n - ns + NTHREADS / 32 - 1) / (NTHREADS / 32);
-      const int ta = min(n, ns + wid * tchunk), tb = min(n, ta + tchunk);
-      T *wbuf = buf + wid * P::WARP_WORDS;
-
-      // the warp's work list: its sorted particles, then its tail share, in pieces of <= PCAP
-      const int nsw = sb - sa, totw = nsw + (tb - ta);
-      int qa = 0, it = 0;
+      // The tile's particles -- [0, ns) sorted by cell, [ns, n) the unsorted tail -- are pushed in
+      // pieces of <= TCAP; inside a piece the rounds of 32 are dealt round-robin to the warps, so
+      // every warp has the same number of rounds whatever its cells hold.
+      T *wbuf = buf;  // parked trajectories of the piece, SoA with stride `tot`
+      int qa = 0;
       bool more = false;
       do {
-        const int qb = min(totw, qa + P::PCAP);
+        const int qb = min(n, qa + P::TCAP);
         const int tot = qb - qa;                          // particles of this piece
-        const int np = max(0, min(qb, nsw) - qa);         // of which sorted: their trajectories are parked
-        const int pa = sa + qa, pb = pa + np;             // sorted particles [pa, pb)
-        const int tp = ta + max(0, qa - nsw) - np;        // tail particle of item m >= np: tp + m
+        const int np = max(0, min(qb, ns) - qa);          // of which sorted: their trajectories are parked
+        const int pa = qa, pb = qa + np;                  // sorted particles [pa, pb)
+        more = qb < n;
         // list of pieces outside their particle's cell, above the parked trajectories: pieces in
         // tile cells grow from the bottom (linked to their cell), halo pieces from the top
-        T *xl = wbuf + P::DW * tot;
-        const int xcap = P::FAST ? (P::WARP_WORDS - P::DW * tot) / P::XW : 0;
+        const int xcap = P::FAST ? (P::BUF_WORDS - P::DW * tot) / P::XW / (NTHREADS / 32) : 0;  // per warp
+        T *xl = wbuf + P::DW * tot + wid * (P::XW * xcap);
         const int xcap_lo = xcap - xcap / 4;
         int nlo = 0, nhi = 0;                         // warp-uniform list lengths
         if (P::FAST && lane == 0) {
@@ -418,7 +415,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         long long ntag_ = 0;
         auto fetch = [&](int m) {
           if (m < tot) {
-            const long long s = off + ((m < np) ? pa + m : tp + m);
+            const long long s = off + qa + m;
 #pragma unroll
             for (int d = 0; d < DIM; d++) nx_[d] = a.sp.x[d][s];
 #pragma unroll
@@ -428,8 +425,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             ntag_ = a.sp.tag[s];
           }
         };
-        fetch(lane);
-        for (int m0 = 0; m0 < tot; m0 += 32) {
+        fetch(32 * wid + lane);
+        for (int m0 = 32 * wid; m0 < tot; m0 += NTHREADS) {
           const int m = m0 + lane;
           const bool active = m < tot, parked = m < np;
           T x[DIM], u[3];
@@ -440,7 +437,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           const T q = nq_;
           const int cell = ncell_;
           const long long tag = ntag_;
-          fetch(m + 32);
+          fetch(m + NTHREADS);
           Seg<DIM, T> seg[DIM + 1];
           int nseg = 0;
           if (active) {
@@ -460,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             int rank = 0;
             if (moved) ncell |= CELL_DEAD;
             else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
-            const long long r = so + ((m < np) ? pa + m : tp + m);
+            const long long r = so + qa + m;
 #pragma unroll
             for (int d = 0; d < DIM; d++) a.scr.x[d][r] = x[d];
 #pragma unroll
@@ -523,7 +520,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
         }
 
-        more = __syncthreads_or(qb < totw);  // every warp's lists are complete
+        __syncthreads();  // every warp's parked trajectories and lists are complete
 
         if constexpr (P::FAST) {
           // -- 2. deposit: one lane per (cell, part) walks the cell's parked trajectories and its
@@ -614,7 +611,6 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         }
         if (more) __syncthreads();  // the next piece reuses the buffers other warps may still read
         qa = qb;
-        it++;
       } while (more);
     }
     __syncthreads();  // J tile, histogram and scratch complete; E/B tile and cs free

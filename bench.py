@@ -237,7 +237,7 @@ def main():
     nd = node_dims(world, dim)
     no_co = NodeConf(dim, nd, [True] * dim, rank)
     sim = Simulation(dim, order, nx, w["dx"], w["dt"], precision=args.prec, nspecies=len(w["species"]),
-                     node_conf=no_co, nccl_id=nccl_id, device=local)
+                     node_conf=no_co, nccl_id=nccl_id, device=local, add_tag=False)  # species{add_tag} default
     gnx = [nx[d] * nd[d] for d in range(dim)]
     off = [no_co.coords[d] * nx[d] for d in range(dim)]
     dt_ = np.float32 if args.prec == "f32" else np.float64

@@ -61,7 +61,9 @@ typedef struct osgpu_config {
   int32_t nranks;     /* reproduced by osgpu_cart_rank)                                  */
   int32_t device;     /* CUDA device ordinal, -1 = rank % device_count                   */
   int32_t smooth_order; /* current smoothing passes folded into gc (0 = none)            */
-  int32_t reserved[7];
+  int32_t no_tags;    /* 1: particles carry no tag (species{add_tag} off, the reference's default,
+                       * spec/os-spec-define.f03:431); by-tag downloads are then unavailable      */
+  int32_t reserved[6];
 } osgpu_config;
 
 /* ---- library / topology helpers (no GPU needed) -------------------------------------- */

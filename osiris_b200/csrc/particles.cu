@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256)
     for (int d = 0; d < 3; d++) sp.p[d][s] = in.p[3 * i + d];
     sp.q[s] = in.q[i];
     sp.cell[s] = c;
-    sp.tag[s] = in.tag ? in.tag[i] : tag_base + i;
+    if (sp.tag) sp.tag[s] = in.tag ? in.tag[i] : tag_base + i;
   }
 }
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256)
     }
     for (int d = 0; d < 3; d++) op[3 * r + d] = sp.p[d][s];
     oq[r] = sp.q[s];
-    if (otag) otag[r] = sp.tag[s];
+    if (otag) otag[r] = sp.tag ? sp.tag[s] : -1;
   }
 }
 
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256)
     }
     for (int d = 0; d < 3; d++) op[3 * r + d] = mv.p[d][i];
     oq[r] = mv.q[i];
-    if (otag) otag[r] = mv.tag[i];
+    if (otag) otag[r] = mv.tag ? mv.tag[i] : -1;
   }
 }
 
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256)
     for (int d = 0; d < 3; d++) sp.p[d][s] = mv.p[d][i];
     sp.q[s] = mv.q[i];
     sp.cell[s] = c;
-    sp.tag[s] = mv.tag[i];
+    if (sp.tag) sp.tag[s] = mv.tag[i];
   }
 }
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256)
     for (int d = 0; d < 3; d++) dst.p[d][dn + i] = src.p[d][so + i];
     dst.q[dn + i] = src.q[so + i];
     dst.cell[dn + i] = src.cell[so + i];
-    dst.tag[dn + i] = src.tag[so + i];
+    if (dst.tag) dst.tag[dn + i] = src.tag[so + i];
   }
 }
 
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256)
     const int k = atomicAdd(&cnt2[side], 1);
     if (k >= cap_rec) { atomicOr(errflag, ERRF_SEND_OVERFLOW); continue; }
     uint32_t *r = (side ? buf_up : buf_lo) + (size_t)k * rw;
-    const long long tag = mv.tag[i];
+    const long long tag = mv.tag ? mv.tag[i] : 0;
     r[0] = (uint32_t)(tag & 0xffffffffll);
     r[1] = (uint32_t)((unsigned long long)tag >> 32);
     T *f = reinterpret_cast<T *>(r + 2);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256)
   if (s_base < 0 || (int)threadIdx.x >= nb) return;
   const int i = first + threadIdx.x, k = s_base + threadIdx.x;
   const uint32_t *r = buf + (size_t)i * rw;
-  mv.tag[k] = (long long)(((unsigned long long)r[1] << 32) | r[0]);
+  if (mv.tag) mv.tag[k] = (long long)(((unsigned long long)r[1] << 32) | r[0]);
   const T *f = reinterpret_cast<const T *>(r + 2);
   for (int d = 0; d < dim; d++) mv.x[d][k] = f[d];
   for (int d = 0; d < 3; d++) mv.p[d][k] = f[dim + d];

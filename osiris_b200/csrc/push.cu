@@ -322,12 +322,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   auto prefetch_particles = [&](int n, long long off) {  // one thread: ask L2 for a tile's columns
     const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(T) + 15) & ~(size_t)15);
 #pragma unroll
-    for (int d = 0; d < DIM; d++) l2_prefetch(a.sp.x[d] + off, bytes);
-#pragma unroll
-    for (int d = 0; d < 3; d++) l2_prefetch(a.sp.p[d] + off, bytes);
-    l2_prefetch(a.sp.q + off, bytes);
-    l2_prefetch(a.sp.cell + off, (uint32_t)(((size_t)n * 4 + 15) & ~(size_t)15));
-    l2_prefetch(a.sp.tag + off, (uint32_t)(((size_t)n * 8 + 15) & ~(size_t)15));
+    for (int c = 0; c < DIM + 4; c++) l2_prefetch(a.spc.base + c * a.spc.stride + off, bytes);
+    l2_prefetch(a.spc.cell + off, (uint32_t)(((size_t)n * 4 + 15) & ~(size_t)15));
+    if (a.spc.tag) l2_prefetch(a.spc.tag + off, (uint32_t)(((size_t)n * 8 + 15) & ~(size_t)15));
   };
 
   if (tid == 0) {
@@ -348,6 +345,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   }
   uint32_t phase = 0;
   double ene = 0.0;
+  T ene_t = T(0);  // per-tile partial in particle precision (the reference sums a chunk in REAL)
   int cur = 0;  // which of the two cell-offset arrays holds the current tile's
   __syncthreads();
   if (P::FAST && s_tile < a.tl.ntile && s_ns > 0) {
@@ -417,12 +415,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           if (m < tot) {
             const long long s = off + qa + m;
 #pragma unroll
-            for (int d = 0; d < DIM; d++) nx_[d] = a.sp.x[d][s];
+            for (int d = 0; d < DIM; d++) nx_[d] = a.spc.base[d * a.spc.stride + s];
 #pragma unroll
-            for (int d = 0; d < 3; d++) nu_[d] = a.sp.p[d][s];
-            nq_ = a.sp.q[s];
-            ncell_ = a.sp.cell[s];
-            ntag_ = a.sp.tag[s];
+            for (int d = 0; d < 3; d++) nu_[d] = a.spc.base[(DIM + d) * a.spc.stride + s];
+            nq_ = a.spc.base[(DIM + 3) * a.spc.stride + s];
+            ncell_ = a.spc.cell[s];
+            if (a.spc.tag) ntag_ = a.spc.tag[s];
           }
         };
         fetch(32 * wid + lane);
@@ -445,7 +443,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
 #pragma unroll
             for (int d = 0; d < DIM; d++) l[d] = cell_l(cell, d);
             const T en = push_one<DIM, ORDER, T>(x, u, l, eb, a.k, seg, &nseg);
-            ene += (double)q * (double)en;
+            ene_t = fmadd(q, en, ene_t);
             bool moved = false;
             int ncell = 0;
 #pragma unroll
@@ -459,13 +457,13 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
             const long long r = so + qa + m;
 #pragma unroll
-            for (int d = 0; d < DIM; d++) a.scr.x[d][r] = x[d];
+            for (int d = 0; d < DIM; d++) a.scc.base[d * a.scc.stride + r] = x[d];
 #pragma unroll
-            for (int d = 0; d < 3; d++) a.scr.p[d][r] = u[d];
-            a.scr.q[r] = q;
-            a.scr.cell[r] = ncell;
-            a.scr.tag[r] = tag;
-            a.scr_rank[r] = rank;
+            for (int d = 0; d < 3; d++) a.scc.base[(DIM + d) * a.scc.stride + r] = u[d];
+            a.scc.base[(DIM + 3) * a.scc.stride + r] = q;
+            a.scc.cell[r] = ncell;
+            if (a.spc.tag) a.scc.tag[r] = tag;
+            a.scc.cell[a.scc.stride + r] = rank;
             if (P::FAST && parked) {
 #pragma unroll
               for (int d = 0; d < DIM; d++) {
@@ -613,9 +611,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         qa = qb;
       } while (more);
     }
+    ene += (double)ene_t;
+    ene_t = T(0);
     __syncthreads();  // J tile, histogram and scratch complete; E/B tile and cs free
 
     // ---- 4. J tile -> HBM; the next tile's E/B loads start ----------------------------------
+    tile_origin(tile, o0);  // (recomputed: not kept in registers through the push)
     if constexpr (P::TMA_J) {
       if (tid == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // atomics -> visible to TMA
@@ -684,68 +685,90 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       pre = g_cs[tid];
       if (tid == 0) pre_last = g_cs[G::NCELL];
     }
-    // four particles per thread in flight: the scratch range sits in L2, latency is what costs
-    for (int i0 = 0; i0 < n; i0 += 4 * NTHREADS) {
-      int cellv[4], rk[4];
-      long long dst[4];
-      bool act[4];
+    // PB particles per thread in flight: the scratch range sits in L2, latency is what costs
+    tile_origin(tile, o0);
+    constexpr int PB = 2;
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += PB * NTHREADS) {
+      int cellv[PB], dst[PB];  // dst: slot in the particle buffer, or ~slot in the mover buffer
+      T vx[PB][DIM], vp[PB][3], vq[PB];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
+      for (int k = 0; k < PB; k++) {
         const int i = i0 + tid + k * NTHREADS;
-        act[k] = i < n;
-        cellv[k] = act[k] ? a.scr.cell[so + i] : 0;
-        rk[k] = act[k] ? a.scr_rank[so + i] : 0;
-      }
-      T vx[4][DIM], vp[4][3], vq[4];
-      long long vt[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (act[k]) {
-          const long long r = so + i0 + tid + k * NTHREADS;
-#pragma unroll
-          for (int d = 0; d < DIM; d++) vx[k][d] = a.scr.x[d][r];
-#pragma unroll
-          for (int d = 0; d < 3; d++) vp[k][d] = a.scr.p[d][r];
-          vq[k] = a.scr.q[r];
-          vt[k] = a.scr.tag[r];
+        cellv[k] = 0;
+        dst[k] = 0;
+        if (i < n) {
+          cellv[k] = a.scc.cell[so + i];
+          dst[k] = a.scc.cell[a.scc.stride + so + i];
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        dst[k] = -1;
-        if (act[k]) {
+      for (int k = 0; k < PB; k++) {
+        const int i = i0 + tid + k * NTHREADS;
+        if (i < n) {
+          const long long r = so + i;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) vx[k][d] = a.scc.base[d * a.scc.stride + r];
+#pragma unroll
+          for (int d = 0; d < 3; d++) vp[k][d] = a.scc.base[(DIM + d) * a.scc.stride + r];
+          vq[k] = a.scc.base[(DIM + 3) * a.scc.stride + r];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PB; k++) {
+        const int i = i0 + tid + k * NTHREADS;
+        if (i >= n) continue;
+        if (cellv[k] < 0) {
+          if (base < 0) continue;  // mover buffer overflow: reported through errflag
+          const int m = base + atomicAdd(&s_mcnt, 1);
+          if (a.spc.tag) a.scc.cell[a.scc.stride + so + i] = m;  // the tag pass below follows
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {
+            a.mvc.base[d * a.mvc.stride + m] = vx[k][d];
+            a.mvc.cell[d * a.mvc.stride + m] = o0[d] + cell_l(cellv[k] & ~CELL_DEAD, d) + 1;
+          }
+#pragma unroll
+          for (int d = 0; d < 3; d++) a.mvc.base[(DIM + d) * a.mvc.stride + m] = vp[k][d];
+          a.mvc.base[(DIM + 3) * a.mvc.stride + m] = vq[k];
+        } else {
+          int l[DIM];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) l[d] = cell_l(cellv[k], d);
+          const long long s = off + hist[linear_cell<DIM>(l)] + dst[k];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) a.spc.base[d * a.spc.stride + s] = vx[k][d];
+#pragma unroll
+          for (int d = 0; d < 3; d++) a.spc.base[(DIM + d) * a.spc.stride + s] = vp[k][d];
+          a.spc.base[(DIM + 3) * a.spc.stride + s] = vq[k];
+          a.spc.cell[s] = cellv[k];
+        }
+      }
+    }
+    if (a.spc.tag) {  // species{add_tag}: the tags follow their particles
+#pragma unroll 1
+      for (int i0 = 0; i0 < n; i0 += PB * NTHREADS) {
+        int cellv[PB], rk[PB];
+        long long vt[PB];
+#pragma unroll
+        for (int k = 0; k < PB; k++) {
+          const int i = i0 + tid + k * NTHREADS;
+          if (i < n) {
+            cellv[k] = a.scc.cell[so + i];
+            rk[k] = a.scc.cell[a.scc.stride + so + i];
+            vt[k] = a.scc.tag[so + i];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < PB; k++) {
+          const int i = i0 + tid + k * NTHREADS;
+          if (i >= n) continue;
           if (cellv[k] < 0) {
-            if (base >= 0) dst[k] = base + atomicAdd(&s_mcnt, 1);
+            if (base >= 0) a.mvc.tag[rk[k]] = vt[k];
           } else {
             int l[DIM];
 #pragma unroll
             for (int d = 0; d < DIM; d++) l[d] = cell_l(cellv[k], d);
-            dst[k] = off + hist[linear_cell<DIM>(l)] + rk[k];
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (dst[k] >= 0) {
-          const long long s = dst[k];
-          if (cellv[k] < 0) {
-#pragma unroll
-            for (int d = 0; d < DIM; d++) {
-              a.mv.x[d][s] = vx[k][d];
-              a.mv.ix[d][s] = o0[d] + cell_l(cellv[k] & ~CELL_DEAD, d) + 1;
-            }
-#pragma unroll
-            for (int d = 0; d < 3; d++) a.mv.p[d][s] = vp[k][d];
-            a.mv.q[s] = vq[k];
-            a.mv.tag[s] = vt[k];
-          } else {
-#pragma unroll
-            for (int d = 0; d < DIM; d++) a.sp.x[d][s] = vx[k][d];
-#pragma unroll
-            for (int d = 0; d < 3; d++) a.sp.p[d][s] = vp[k][d];
-            a.sp.q[s] = vq[k];
-            a.sp.cell[s] = cellv[k];
-            a.sp.tag[s] = vt[k];
+            a.spc.tag[off + hist[linear_cell<DIM>(l)] + rk[k]] = vt[k];
           }
         }
       }

@@ -12,15 +12,24 @@ struct alignas(64) TmaMaps {
   CUtensorMap m[9];
 };
 
+// SoA columns at a constant stride, as the kernel addresses them (one base pointer per buffer):
+// real column c of slot s is base[c * stride + s] -- x(D), p(3), q in this order; `cell` is the first
+// int column behind them (species / scratch: packed cell, scratch: + rank one stride further;
+// movers: ix(D)); `tag` is null when the species carries no tags
+template <typename T> struct Cols {
+  T *base;
+  long long stride;
+  int *cell;
+  long long *tag;
+};
+
 template <typename T> struct PushArgs {
-  SpeciesView<T> sp;
-  MoverView<T> mv;
+  Cols<T> spc, scc, mvc;  // species buffer, per-CTA scratch ranges, mover buffer
+  MoverView<T> mv;        // (count, cap)
   const int *tile_off;
   int *tile_cnt;
   int *tile_nsorted;    // the first tile_nsorted[t] particles of tile t are sorted by cell
   int *cell_start;      // [ntile][TILE_NCELL + 1] offsets of the cells inside the sorted range
-  SpeciesView<T> scr;   // scratch columns: one range of scr_stride slots per CTA
-  int *scr_rank;
   int scr_stride;
   int *tile_counter;    // persistent CTAs take tiles from here (zeroed before the launch)
   T *J[3];

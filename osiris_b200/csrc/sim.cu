@@ -249,9 +249,9 @@ template <typename T> struct Sim final : SimBase {
   // the push kernel's scratch)
   static size_t slot_bytes(int dim) { return (dim + 4) * sizeof(T) + 2 * sizeof(int) + sizeof(long long); }
   static size_t species_bytes(int dim, long long cap) { return (size_t)cap * slot_bytes(dim); }
-  static void carve(void *mem, int dim, long long cap, SpeciesView<T> *v) {
+  void carve(void *mem, int dim, long long cap, SpeciesView<T> *v) const {
     char *p = (char *)mem;
-    v->tag = (long long *)p; p += cap * sizeof(long long);
+    v->tag = cfg.no_tags ? nullptr : (long long *)p; p += cap * sizeof(long long);
     for (int d = 0; d < 3; d++) {
       v->x[d] = nullptr;
       if (d < dim) { v->x[d] = (T *)p; p += cap * sizeof(T); }
@@ -260,11 +260,6 @@ template <typename T> struct Sim final : SimBase {
     v->q = (T *)p; p += cap * sizeof(T);
     v->cell = (int *)p;
   }
-  // the same memory seen as `cap` scratch slots with a rank column
-  static int *carve_rank(void *mem, int dim, long long cap) {
-    return (int *)((char *)mem + (size_t)cap * (slot_bytes(dim) - sizeof(int)));
-  }
-
   int species_create(int id, double rqm, long long np_max) override {
     if (id < 0 || id >= (int)sp.size()) { set_error("species id %d out of range", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
@@ -292,7 +287,7 @@ template <typename T> struct Sim final : SimBase {
     const size_t per = (dim + 4) * sizeof(T) + (dim + 2) * sizeof(int) + sizeof(long long);
     OSGPU_CUDA(cudaMalloc(&s.mvmem, per * s.mv.cap + sizeof(int) * 4));
     char *p = (char *)s.mvmem;
-    s.mv.tag = (long long *)p; p += sizeof(long long) * s.mv.cap;
+    s.mv.tag = cfg.no_tags ? nullptr : (long long *)p; p += sizeof(long long) * s.mv.cap;
     for (int d = 0; d < 3; d++) { s.mv.x[d] = nullptr; if (d < dim) { s.mv.x[d] = (T *)p; p += sizeof(T) * s.mv.cap; } }
     for (int d = 0; d < 3; d++) { s.mv.p[d] = (T *)p; p += sizeof(T) * s.mv.cap; }
     s.mv.q = (T *)p; p += sizeof(T) * s.mv.cap;
@@ -430,6 +425,7 @@ template <typename T> struct Sim final : SimBase {
   int species_download(int id, int *ix, void *x, void *p, void *q, long long *tag, int by_tag) override {
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
+    if (by_tag && cfg.no_tags) { set_error("species %d carries no tags (no_tags): by-tag download unavailable", id); return OSGPU_ERR_INVALID; }
     std::vector<int> cnt(tl.ntile);
     OSGPU_CUDA(cudaMemcpyAsync(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile, cudaMemcpyDeviceToHost, st));
     OSGPU_CUDA(cudaMemcpyAsync(h_pin + 8, s.mv.count, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -551,8 +547,10 @@ template <typename T> struct Sim final : SimBase {
       if (!s.created) continue;
       if (s.movers_pending) { set_error("advance_deposit called twice without particles_update_boundary"); return OSGPU_ERR_INVALID; }
       PushArgs<T> a;
-      a.sp = s.v[s.cur];
+      const SpeciesView<T> &cv = s.v[s.cur];
+      a.spc.base = cv.x[0]; a.spc.stride = s.cap; a.spc.cell = cv.cell; a.spc.tag = cv.tag;
       a.mv = s.mv;
+      a.mvc.base = s.mv.x[0]; a.mvc.stride = s.mv.cap; a.mvc.cell = s.mv.ix[0]; a.mvc.tag = s.mv.tag;
       a.tile_off = s.tile_off[s.cur];
       a.tile_cnt = s.tile_cnt;
       a.tile_nsorted = s.tile_nsorted;
@@ -561,9 +559,10 @@ template <typename T> struct Sim final : SimBase {
       // persistent CTAs; each owns one scratch range (widest tile) carved from the idle buffer
       int nblocks = std::min(tl.ntile, n_sm * push_bps);
       while (nblocks > 1 && (long long)nblocks * s.max_range > s.cap) nblocks--;
-      const long long nscr = (long long)nblocks * s.max_range;
-      carve(s.mem[1 - s.cur], dim, nscr, &a.scr);
-      a.scr_rank = carve_rank(s.mem[1 - s.cur], dim, nscr);
+      const long long nscr = std::max<long long>((long long)nblocks * s.max_range, 1);
+      SpeciesView<T> sv;
+      carve(s.mem[1 - s.cur], dim, nscr, &sv);
+      a.scc.base = sv.x[0]; a.scc.stride = nscr; a.scc.cell = sv.cell; a.scc.tag = sv.tag;  // rank: cell + stride
       a.scr_stride = s.max_range;
       OSGPU_CUDA(cudaMemsetAsync(s.tile_counter, 0, sizeof(int), st));
       for (int k = 0; k < 3; k++) a.J[k] = J.c[k];

@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("dx", C.c_double * 3), ("dt", C.c_double),
         ("node_dims", C.c_int32 * 3), ("node_coords", C.c_int32 * 3), ("periodic", C.c_int32 * 3),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32), ("smooth_order", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("no_tags", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

@@ -159,7 +159,7 @@ class Simulation:
     """The hot part of t_simulation (os-simulation.f03).  One instance per rank / GPU."""
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
-                 node_conf=None, nccl_id=None, device=-1, smooth_order=0):
+                 node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
@@ -183,6 +183,8 @@ class Simulation:
             cfg.periodic[d] = int(self.no_co.if_periodic[d])
         cfg.dt = self.dt
         cfg.rank, cfg.nranks, cfg.device, cfg.smooth_order = self.no_co.rank, self.no_co.nranks, device, smooth_order
+        cfg.no_tags = 0 if add_tag else 1  # species{add_tag} (spec/os-spec-define.f03:431)
+        self.add_tag = bool(add_tag)
         self._cfg = cfg
         self._h = C.c_void_p()
         idbuf = None

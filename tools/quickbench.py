@@ -6,7 +6,7 @@ name = sys.argv[1] if len(sys.argv)>1 else 'uniform3d'
 scale = float(sys.argv[2]) if len(sys.argv)>2 else 1.0
 w = dict(WORKLOADS[name])
 nx = [int(n*scale) for n in w['nx']]
-sim = Simulation(w['dim'], w['order'], nx, w['dx'], w['dt'], nspecies=len(w['species']))
+sim = Simulation(w['dim'], w['order'], nx, w['dx'], w['dt'], nspecies=len(w['species']), add_tag=os.environ.get('TAGS','0')=='1')
 npart = 0
 t0=time.time()
 for i,s in enumerate(w['species']):

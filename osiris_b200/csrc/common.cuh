@@ -56,14 +56,18 @@ template <typename T> struct Field3 {
   T *c[3];
 };
 
-// Struct-of-arrays particle buffer of one species, tile-binned: tile t owns slots
-// [tile_off[t], tile_off[t+1]) of which the first tile_cnt[t] are live.
+// Particle buffer of one species, tile-binned: tile t owns slots [tile_off[t], tile_off[t+1]) of
+// which the first tile_cnt[t] are live.  The real columns x(D) p(3) q are stored struct-of-arrays
+// inside blocks of 32 slots: column c of slot s sits at base[((s / 32) * nc + c) * 32 + s % 32], so
+// the 32 particles a warp handles in one round are nc consecutive 128-byte (fp32) rows -- one
+// contiguous range for a TMA bulk copy, and constant row offsets from one per-lane address.
 template <typename T> struct SpeciesView {
-  T *x[3];
-  T *p[3];
-  T *q;
-  int *cell;        // packed tile-local cell (tile.cuh)
-  long long *tag;
+  T *base;
+  int nc;           // real columns per slot: dim + 4
+  int *cell;        // packed tile-local cell (tile.cuh), one int per slot
+  long long *tag;   // null when the species carries no tags
+  __host__ __device__ __forceinline__ long long blk(long long s) const { return (((s >> 5) * nc) << 5) + (s & 31); }
+  __host__ __device__ __forceinline__ T &r(int c, long long s) const { return base[blk(s) + 32 * c]; }
 };
 
 // Particles that left their tile (or the rank) during a push: global ix, SoA.

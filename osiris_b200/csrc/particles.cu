@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(256)
     int t, c;
     if (!locate(ix, dim, tl, g.nx, &t, &c)) continue;
     const long long s = (long long)tile_off[t] + atomicAdd(&cursor[t], 1);
-    for (int d = 0; d < dim; d++) sp.x[d][s] = in.x[dim * i + d];
-    for (int d = 0; d < 3; d++) sp.p[d][s] = in.p[3 * i + d];
-    sp.q[s] = in.q[i];
+    for (int d = 0; d < dim; d++) sp.r(d, s) = in.x[dim * i + d];
+    for (int d = 0; d < 3; d++) sp.r(dim + d, s) = in.p[3 * i + d];
+    sp.r(dim + 3, s) = in.q[i];
     sp.cell[s] = c;
     if (sp.tag) sp.tag[s] = in.tag ? in.tag[i] : tag_base + i;
   }
@@ -82,11 +82,11 @@ __global__ void __launch_bounds__(256)
     const long long s = off + i, r = by_tag ? sp.tag[s] : o + i;
     const int cell = sp.cell[s];
     for (int d = 0; d < dim; d++) {
-      ox[dim * r + d] = sp.x[d][s];
+      ox[dim * r + d] = sp.r(d, s);
       oix[dim * r + d] = tc[d] * tl.T[d] + cell_l(cell, d) + 1;
     }
-    for (int d = 0; d < 3; d++) op[3 * r + d] = sp.p[d][s];
-    oq[r] = sp.q[s];
+    for (int d = 0; d < 3; d++) op[3 * r + d] = sp.r(dim + d, s);
+    oq[r] = sp.r(dim + 3, s);
     if (otag) otag[r] = sp.tag ? sp.tag[s] : -1;
   }
 }
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(256)
     int t, c;
     if (!locate(ix, dim, tl, g.nx, &t, &c)) continue;
     const long long s = (long long)tile_off[t] + atomicAdd(&tile_cnt[t], 1);
-    for (int d = 0; d < dim; d++) sp.x[d][s] = mv.x[d][i];
-    for (int d = 0; d < 3; d++) sp.p[d][s] = mv.p[d][i];
-    sp.q[s] = mv.q[i];
+    for (int d = 0; d < dim; d++) sp.r(d, s) = mv.x[d][i];
+    for (int d = 0; d < 3; d++) sp.r(dim + d, s) = mv.p[d][i];
+    sp.r(dim + 3, s) = mv.q[i];
     sp.cell[s] = c;
     if (sp.tag) sp.tag[s] = mv.tag[i];
   }
@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(256)
   const int n = tile_cnt[tile];
   const long long so = old_off[tile], dn = new_off[tile];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    for (int d = 0; d < dim; d++) dst.x[d][dn + i] = src.x[d][so + i];
-    for (int d = 0; d < 3; d++) dst.p[d][dn + i] = src.p[d][so + i];
-    dst.q[dn + i] = src.q[so + i];
+    for (int d = 0; d < dim; d++) dst.r(d, dn + i) = src.r(d, so + i);
+    for (int d = 0; d < 3; d++) dst.r(dim + d, dn + i) = src.r(dim + d, so + i);
+    dst.r(dim + 3, dn + i) = src.r(dim + 3, so + i);
     dst.cell[dn + i] = src.cell[so + i];
     if (dst.tag) dst.tag[dn + i] = src.tag[so + i];
   }

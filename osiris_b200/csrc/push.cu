@@ -91,6 +91,11 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, const 
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void l2_prefetch(const void *p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -122,20 +127,31 @@ __device__ __forceinline__ int block_scan(int v, int *total, int *s_warp) {
 // shared-memory plan of one instantiation
 template <int DIM, int ORDER, typename T> struct Plan {
   using G = Tile<DIM, ORDER, T>;
-  // orders 1-2: the in-cell piece of every sorted particle is accumulated in registers per cell
-  // (12 / 54 values in 3D); orders 3-4 would need 144 / 300 registers and deposit directly
+  // orders 1-2: the particles of a tile are staged in shared memory by TMA bulk copies and the
+  // in-cell piece of every sorted particle is accumulated in registers per cell (12 / 54 values in
+  // 3D); orders 3-4 would need 144 / 300 registers: they load from global memory and deposit directly
   static constexpr bool FAST = ORDER <= 2;
-  static constexpr int DW = (DIM == 2) ? 6 : 7;  // parked trajectory: x0[D], x1[D], q, (vz)
-  static constexpr int XW = DW + 1;              // listed piece: + packed tile-local cell
-  // one buffer per CTA: the parked trajectories of a piece from the bottom, above them one list
-  // region per warp
+  static constexpr int NWARP = NTHREADS / 32;
+  static constexpr int NC = DIM + 4;            // staged columns: x(D) u(3) q, blocked by 32 slots
+  static constexpr int CHUNK_WORDS = NC * 32;   // one block of 32 slots
+  static constexpr int XW = NC + 1;             // listed piece: p0[D], p1[D], q, (vz), link
+  static constexpr int QN = 64;                 // crosser queue entries per warp (ints)
+  static constexpr int QWORDS = QN * 4 / (int)sizeof(T);
+  // one buffer per CTA: the staged particles of a piece from the bottom (after the push the
+  // momentum slots hold the end point of the trajectory), above them one region per warp with the
+  // list of pieces that belong to other cells of the tile and the queue of particles to split, and
+  // at the top the CTA's list of pieces that lie in halo cells
   static constexpr int BUF_BYTES = FAST ? 74752 : 0;
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
-  static constexpr int XMIN = 40 * (NTHREADS / 32);  // list entries always available
-  static constexpr int TCAP = FAST ? (((BUF_WORDS - XMIN * XW) / DW) & ~255) : (1 << 30);
+  static constexpr int XMIN = 20;  // list entries per warp always available
+  static constexpr int HCAP = 96;  // CTA-wide list of pieces in halo cells (top of the buffer)
+  static constexpr int TCAP = FAST ? (((BUF_WORDS - NWARP * (XMIN * XW + QWORDS) - HCAP * XW) / NC) & ~255) : (1 << 30);
+  static constexpr int NROUND = FAST ? TCAP / NTHREADS : 1;
+  static_assert(NROUND <= 16, "one mbarrier (and one phase bit) per staged round");
+  static_assert(!FAST || TCAP < 4096, "queue entries keep the slot in 12 bits");
   static constexpr int NACC = 3 * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
   static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
-  static constexpr int OFF_BUF = OFF_JT + round_up(3 * G::JVOL * (int)sizeof(T), 16);
+  static constexpr int OFF_BUF = round_up(OFF_JT + 3 * G::JVOL * (int)sizeof(T), 128);
   static constexpr int OFF_CS = OFF_BUF + BUF_BYTES;
   static constexpr int CS_STRIDE = round_up(G::NCELL + 1, 4);
   static constexpr int OFF_HIST = OFF_CS + 2 * CS_STRIDE * 4;
@@ -146,6 +162,8 @@ template <int DIM, int ORDER, typename T> struct Plan {
   PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {
     return ((comp * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
   }
+  // word offset of staged slot m (column 0) inside the buffer
+  PIC_HD static int slot(int m) { return (m >> 5) * CHUNK_WORDS + (m & 31); }
 };
 
 template <int DIM> __device__ __forceinline__ int linear_cell(const int *l) {
@@ -176,78 +194,36 @@ template <typename T, int N> __device__ __forceinline__ void add_batch(T *const 
     if (!cas_add(p[k], old[k], v[k])) atomicAdd(p[k], v[k]);
 }
 
-// Flush of the per-cell stencil accumulators when the 32 lanes of a warp hold 32 consecutive cells
-// (rows of TX cells along x).  The stencils of x-neighbours overlap: the lane that owns a grid
-// column (the one whose entry k1 = KO lands there) collects its neighbours' entries for that
-// column with shuffles and issues the only shared-memory update; entries whose owner would lie
-// outside the row are added by the lane itself.  Updates are issued in batches of one y-row of
-// the stencil (k2 fixed): inside a batch no two lanes of the warp touch the same word.
+// Flush of a cell's stencil accumulators into the shared J tile: one batch per component and z
+// plane (inside a batch the addresses of a lane are distinct; lanes of a warp hold unrelated cells,
+// an update that collides with another lane's falls back to the atomic).
 template <int DIM, int ORDER, typename T, class P>
-__device__ __forceinline__ void flush_merged(const T *acc, T *pj, int x) {
+__device__ __forceinline__ void flush_stencil(const T *acc, T *pj) {
   using G = Tile<DIM, ORDER, T>;
   constexpr int NP = G::NP;
-  constexpr unsigned FULL = 0xffffffffu;
   constexpr int NZ = (DIM == 3) ? NP : 1;
-  // entries along x and the owner entry, per component
-  constexpr int NK1[3] = {NP - 1, NP, NP};
-  constexpr int KO[3] = {(NP - 2 < 1) ? NP - 2 : 1, (NP - 1 < 1) ? NP - 1 : 1, (NP - 1 < 1) ? NP - 1 : 1};
 #pragma unroll
-  for (int k2 = 0; k2 < NP; k2++) {
-    // -- columns owned by this lane --
-    constexpr int NZ2 = (DIM == 3) ? NZ - 1 : NZ;  // component-3 entries per row
-    constexpr int NB = 2 * NZ + NZ2;               // entries of a row (the last row has no component 2)
-    T *bp[NB];
-    T bv[NB];
-    int nb = 0;
+  for (int comp = 0; comp < 3; comp++) {
+    constexpr int N1[3] = {NP - 1, NP, NP}, N2[3] = {NP, NP - 1, NP};
 #pragma unroll
-    for (int comp = 0; comp < 3; comp++) {
-      if (comp == 1 && k2 >= NP - 1) continue;
+    for (int k3 = 0; k3 < NZ; k3++) {
+      if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
+      const int n1 = N1[comp], n2 = N2[comp];
+      T *bp[NP * NP];
+      T bv[NP * NP];
 #pragma unroll
-      for (int k3 = 0; k3 < NZ; k3++) {
-        if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
-        const int nk1 = NK1[comp], ko = KO[comp];
-        T m = acc[P::acc_index(comp, ko, k2, k3)];
-#pragma unroll
-        for (int d = 1; d <= ko; d++) {  // entry ko - d of the lane d cells to the right
-          const T t = __shfl_down_sync(FULL, acc[P::acc_index(comp, ko - d, k2, k3)], d);
-          if (x + d < G::TX) m += t;
-        }
-#pragma unroll
-        for (int d = 1; d <= nk1 - 1 - ko; d++) {  // entry ko + d of the lane d cells to the left
-          const T t = __shfl_up_sync(FULL, acc[P::acc_index(comp, ko + d, k2, k3)], d);
-          if (x - d >= 0) m += t;
-        }
-        bp[nb] = pj + comp * G::JVOL + G::JX * (k2 + G::JY * k3) + ko;
-        bv[nb] = m;
-        nb++;
+      for (int k = 0; k < NP * NP; k++) {  // (entries beyond n1 * n2 repeat the last one with a zero)
+        const int k1 = (k < n1 * n2) ? k % n1 : 0, k2 = (k < n1 * n2) ? k / n1 : 0;
+        bp[k] = pj + comp * G::JVOL + k1 + G::JX * (k2 + G::JY * k3);
+        bv[k] = acc[P::acc_index(comp, k1, k2, k3)];
       }
-    }
-    if (k2 < NP - 1) add_batch<T, NB>(bp, bv);
-    else {  // the last row has no component-1 entries
-      T *cp[NB - NZ];
-      T cv[NB - NZ];
+      if (comp == 2) add_batch<T, NP * NP>(bp, bv);
+      else {
+        T *cp[NP * (NP - 1)];
+        T cv[NP * (NP - 1)];
 #pragma unroll
-      for (int k = 0; k < NB - NZ; k++) { cp[k] = bp[k]; cv[k] = bv[k]; }
-      add_batch<T, NB - NZ>(cp, cv);
-      static_assert(NB - NZ == NZ + NZ2, "row without component-2 entries");
-    }
-    // -- columns whose owner cell lies outside the row: first and last lane of the row --
-    if (x == 0 || x == G::TX - 1) {
-#pragma unroll
-      for (int comp = 0; comp < 3; comp++) {
-        if (comp == 1 && k2 >= NP - 1) continue;
-#pragma unroll
-        for (int k3 = 0; k3 < NZ; k3++) {
-          if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
-          const int nk1 = NK1[comp], ko = KO[comp];
-#pragma unroll
-          for (int k1 = 0; k1 < nk1; k1++) {
-            if (k1 == ko) continue;
-            const int xo = x + k1 - ko;  // owner cell of this column
-            if (xo < 0 || xo >= G::TX)
-              atomicAdd(pj + comp * G::JVOL + G::JX * (k2 + G::JY * k3) + k1, acc[P::acc_index(comp, k1, k2, k3)]);
-          }
-        }
+        for (int k = 0; k < NP * (NP - 1); k++) { cp[k] = bp[k]; cv[k] = bv[k]; }
+        add_batch<T, NP * (NP - 1)>(cp, cv);
       }
     }
   }
@@ -258,6 +234,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     push_deposit_kernel(const __grid_constant__ TmaMaps maps, const PushArgs<T> a) {
   using G = Tile<DIM, ORDER, T>;
   using P = Plan<DIM, ORDER, T>;
+  constexpr int NC = P::NC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   T *eb = reinterpret_cast<T *>(smem_raw);
   T *jt = reinterpret_cast<T *>(smem_raw + P::OFF_JT);
@@ -265,9 +242,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   int *cs2 = reinterpret_cast<int *>(smem_raw + P::OFF_CS);  // two arrays: current / next tile
   int *hist = reinterpret_cast<int *>(smem_raw + P::OFF_HIST);
   int *heads = reinterpret_cast<int *>(smem_raw + P::OFF_HEADS);  // per cell: list of foreign pieces
-  __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t mbar;                 // E/B tile
+  __shared__ __align__(8) uint64_t mbar_p[P::NROUND];    // staged particles, one per round of 256
   __shared__ int s_xl[NTHREADS / 32], s_xcap[NTHREADS / 32];
-  __shared__ int s_tile, s_n, s_ns, s_mcnt, s_base;
+  __shared__ int s_tile, s_n, s_ns, s_mcnt, s_base, s_nh, s_arrive, s_sortc;
   __shared__ long long s_off, s_next_off;
   __shared__ int s_next[3];
   __shared__ int s_warp[NTHREADS / 32];
@@ -280,9 +258,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   const long long so = (long long)blockIdx.x * a.scr_stride;
 
   // Tile bookkeeping is pipelined: while a tile is pushed, one thread has already taken the CTA's
-  // next tile from the device counter and asked L2 for its particle columns; as soon as the push
-  // is over (E/B tile free) the same thread starts the next tile's TMA loads, which then overlap
-  // the J write-back and the sort of the current tile.
+  // next tile from the device counter; as soon as the deposit is over (E/B tile and particle
+  // buffer free) the same thread starts the next tile's TMA loads -- fields and particles -- which
+  // then overlap the J write-back and the sort of the current tile.
   auto take_tile = [&](int *n_out, int *ns_out, long long *off_out) {  // skips empty tiles
     int t;
     for (;;) {
@@ -319,18 +297,32 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       else tma_load_3d(eb + c * G::ESTRIDE, &maps.m[c], &mbar, c0, c1, c2);
     }
   };
-  auto prefetch_particles = [&](int n, long long off) {  // one thread: ask L2 for a tile's columns
-    const uint32_t bytes = (uint32_t)(((size_t)n * sizeof(T) + 15) & ~(size_t)15);
-#pragma unroll
-    for (int c = 0; c < DIM + 4; c++) l2_prefetch(a.spc.base + c * a.spc.stride + off, bytes);
+  // one thread: bulk copies of `cnt` particles from slot `slot0` (a multiple of 32) into the
+  // buffer, one copy and one mbarrier per round of 256 particles (whole blocks of 32 slots)
+  auto stage_particles = [&](long long slot0, int cnt) {
+    const int nch = (cnt + 31) >> 5;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic writes to the buffer
+    const T *src = a.spc.base + (slot0 >> 5) * P::CHUNK_WORDS;
+    for (int r = 0; 8 * r < nch; r++) {
+      const uint32_t bytes = (uint32_t)min(8, nch - 8 * r) * (uint32_t)(P::CHUNK_WORDS * sizeof(T));
+      mbar_expect_tx(&mbar_p[r], bytes);
+      bulk_load(buf + 8 * r * P::CHUNK_WORDS, src + 8 * r * P::CHUNK_WORDS, bytes, &mbar_p[r]);
+    }
+  };
+  auto prefetch_particles = [&](int n, long long off) {  // one thread: ask L2 for a tile's particles
+    l2_prefetch(a.spc.base + (off >> 5) * P::CHUNK_WORDS, (uint32_t)(((n + 31) >> 5) * P::CHUNK_WORDS * sizeof(T)));
     l2_prefetch(a.spc.cell + off, (uint32_t)(((size_t)n * 4 + 15) & ~(size_t)15));
-    if (a.spc.tag) l2_prefetch(a.spc.tag + off, (uint32_t)(((size_t)n * 8 + 15) & ~(size_t)15));
   };
 
   if (tid == 0) {
     mbar_init(&mbar, 1);
+#pragma unroll
+    for (int r = 0; r < P::NROUND; r++) mbar_init(&mbar_p[r], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_mcnt = 0;
+    s_nh = 0;
+    s_arrive = 0;
+    s_sortc = 0;
   }
   for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
   hist[tid] = 0;
@@ -341,9 +333,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     long long off = 0;
     const int t = take_tile(&n, &ns, &off);
     s_tile = t; s_n = n; s_ns = ns; s_off = off;
-    if (t < a.tl.ntile) stage_fields(t);
+    if (t < a.tl.ntile) {
+      stage_fields(t);
+      if (P::FAST) stage_particles(off, min(n, P::TCAP));
+    }
   }
-  uint32_t phase = 0;
+  uint32_t phase = 0, pph = 0;  // mbarrier parities: E/B tile, staged rounds (one bit each)
   double ene = 0.0;
   T ene_t = T(0);  // per-tile partial in particle precision (the reference sums a chunk in REAL)
   int cur = 0;  // which of the two cell-offset arrays holds the current tile's
@@ -362,17 +357,17 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     const long long off = s_off;
     int *cs = cs2 + cur * P::CS_STRIDE;
 
-    int o0[3], tlim[3];
+    int o0[3], tlim[3], nlive = 0;
     tile_origin(tile, o0);
 #pragma unroll
     for (int d = 0; d < 3; d++) tlim[d] = min(a.tl.T[d], a.g.nx[d] - o0[d]);
 
-    // the CTA's next tile: taken now, its particle columns requested from L2, used at the end
+    // the CTA's next tile: taken now, used at the end
     if (tid == 32) {
       int nx_n = 0, nx_ns = 0;
       long long nx_off = 0;
       const int nx_tile = take_tile(&nx_n, &nx_ns, &nx_off);
-      if (nx_tile < a.tl.ntile) prefetch_particles(nx_n, nx_off);
+      if (!P::FAST && nx_tile < a.tl.ntile) prefetch_particles(nx_n, nx_off);
       s_next[0] = nx_tile; s_next[1] = nx_n; s_next[2] = nx_ns; s_next_off = nx_off;
     }
     mbar_wait(&mbar, phase);
@@ -383,102 +378,70 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     {
       constexpr unsigned FULL = 0xffffffffu;
       const unsigned lt_mask = (1u << lane) - 1u;
-      const int c_lo = 32 * wid;
       // The tile's particles -- [0, ns) sorted by cell, [ns, n) the unsorted tail -- are pushed in
       // pieces of <= TCAP; inside a piece the rounds of 32 are dealt round-robin to the warps, so
       // every warp has the same number of rounds whatever its cells hold.
-      T *wbuf = buf;  // parked trajectories of the piece, SoA with stride `tot`
       int qa = 0;
       bool more = false;
       do {
         const int qb = min(n, qa + P::TCAP);
         const int tot = qb - qa;                          // particles of this piece
-        const int np = max(0, min(qb, ns) - qa);          // of which sorted: their trajectories are parked
+        const int np = max(0, min(qb, ns) - qa);          // of which sorted: their trajectories are walked per cell
         const int pa = qa, pb = qa + np;                  // sorted particles [pa, pb)
+        const int nrounds = (tot + NTHREADS - 1) / NTHREADS;
         more = qb < n;
-        // list of pieces outside their particle's cell, above the parked trajectories: pieces in
-        // tile cells grow from the bottom (linked to their cell), halo pieces from the top
-        const int xcap = P::FAST ? (P::BUF_WORDS - P::DW * tot) / P::XW / (NTHREADS / 32) : 0;  // per warp
-        T *xl = wbuf + P::DW * tot + wid * (P::XW * xcap);
-        const int xcap_lo = xcap - xcap / 4;
-        int nlo = 0, nhi = 0;                         // warp-uniform list lengths
+        // above the staged particles: per warp a list of trajectory pieces that lie in other cells
+        // of the tile (linked to their cell) and the queue of particles whose trajectory is split
+        const int xbase = NC * ((tot + 31) & ~31);
+        const int wregion = P::FAST ? ((P::BUF_WORDS - P::HCAP * P::XW - xbase) / P::NWARP) & ~3 : 0;
+        const int xcap = P::FAST ? (wregion - P::QWORDS) / P::XW : 0;  // list entries per warp
+        T *xl = buf + xbase + wid * wregion;
+        int *queue = reinterpret_cast<int *>(xl + P::XW * xcap);
+        T *hl = buf + P::BUF_WORDS - P::HCAP * P::XW;  // halo pieces, SoA with stride HCAP
+        int nlo = 0, ncq = 0;  // warp-uniform: list length, queue length
         if (P::FAST && lane == 0) {
           s_xl[wid] = (int)(xl - buf);
           s_xcap[wid] = xcap;
         }
 
-        // -- 1. push, 32 particles per round; the next round's loads are issued first ----------
-        T nx_[DIM], nu_[3], nq_ = T(0);
-        int ncell_ = 0;
-        long long ntag_ = 0;
-        auto fetch = [&](int m) {
-          if (m < tot) {
-            const long long s = off + qa + m;
-#pragma unroll
-            for (int d = 0; d < DIM; d++) nx_[d] = a.spc.base[d * a.spc.stride + s];
-#pragma unroll
-            for (int d = 0; d < 3; d++) nu_[d] = a.spc.base[(DIM + d) * a.spc.stride + s];
-            nq_ = a.spc.base[(DIM + 3) * a.spc.stride + s];
-            ncell_ = a.spc.cell[s];
-            if (a.spc.tag) ntag_ = a.spc.tag[s];
-          }
-        };
-        fetch(32 * wid + lane);
-        for (int m0 = 32 * wid; m0 < tot; m0 += NTHREADS) {
-          const int m = m0 + lane;
-          const bool active = m < tot, parked = m < np;
-          T x[DIM], u[3];
-#pragma unroll
-          for (int d = 0; d < DIM; d++) x[d] = nx_[d];
-#pragma unroll
-          for (int d = 0; d < 3; d++) u[d] = nu_[d];
-          const T q = nq_;
-          const int cell = ncell_;
-          const long long tag = ntag_;
-          fetch(m + NTHREADS);
+        // split the queued trajectories [qbase, qbase + cnt) of this warp, one per lane: the piece
+        // in the particle's own cell goes back to its staged slot (sorted particles), the others to
+        // the list of their cell, or straight into the J tile when they lie in the halo
+        auto split_queued = [&](int qbase, int cnt) {
+          __syncwarp();
+          const bool have = lane < cnt;
           Seg<DIM, T> seg[DIM + 1];
           int nseg = 0;
-          if (active) {
-            int l[DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; d++) l[d] = cell_l(cell, d);
-            const T en = push_one<DIM, ORDER, T>(x, u, l, eb, a.k, seg, &nseg);
-            ene_t = fmadd(q, en, ene_t);
-            bool moved = false;
-            int ncell = 0;
+          bool tail = false;
+          T q = T(0);
+          if (have) {
+            const int ent = queue[qbase + lane];
+            const int m = ent & 4095, lc = (ent >> 12) & 255;
+            tail = (ent >> 20) & 1;
+            T *pb_ = buf + P::slot(m);
+            int di[3] = {0, 0, 0};
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
-              moved |= (l[d] < 0) || (l[d] >= tlim[d]);
-              ncell |= (l[d] + 1) << (d * CELL_BITS);
+              seg[0].p0[d] = pb_[32 * d];
+              seg[0].p1[d] = pb_[32 * (DIM + d)];
+              di[d] = ntrim<T>(seg[0].p1[d]);
             }
-            if (DIM == 2) ncell |= 1 << (2 * CELL_BITS);
-            int rank = 0;
-            if (moved) ncell |= CELL_DEAD;
-            else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
-            const long long r = so + qa + m;
+            q = pb_[32 * (DIM + 3)];
+            if (DIM == 2) seg[0].vz = pb_[32 * (DIM + 2)];
+            seg[0].c[0] = lc % G::TX;
+            seg[0].c[1] = (lc / G::TX) % G::TY;
+            if (DIM == 3) seg[0].c[DIM - 1] = lc / (G::TX * G::TY);
+            nseg = split_trajectory<DIM, T>(seg, di);
+            if (!tail) {
 #pragma unroll
-            for (int d = 0; d < DIM; d++) a.scc.base[d * a.scc.stride + r] = x[d];
-#pragma unroll
-            for (int d = 0; d < 3; d++) a.scc.base[(DIM + d) * a.scc.stride + r] = u[d];
-            a.scc.base[(DIM + 3) * a.scc.stride + r] = q;
-            a.scc.cell[r] = ncell;
-            if (a.spc.tag) a.scc.tag[r] = tag;
-            a.scc.cell[a.scc.stride + r] = rank;
-            if (P::FAST && parked) {
-#pragma unroll
-              for (int d = 0; d < DIM; d++) {
-                wbuf[d * tot + m] = seg[0].p0[d];
-                wbuf[(DIM + d) * tot + m] = seg[0].p1[d];
-              }
-              wbuf[2 * DIM * tot + m] = q;
-              if (DIM == 2) wbuf[(2 * DIM + 1) * tot + m] = seg[0].vz;
+              for (int d = 0; d < DIM; d++) pb_[32 * (DIM + d)] = seg[0].p1[d];
+              if (DIM == 2) pb_[32 * (DIM + 2)] = seg[0].vz;
             }
           }
-          // pieces outside the particle's own cell (and every piece of a tail particle)
           unsigned direct = 0;
 #pragma unroll
           for (int k = 0; k <= DIM; k++) {
-            const bool has = active && (k < nseg) && (k > 0 || !(P::FAST && parked));
+            const bool has = have && (k < nseg) && (k > 0 || tail);
             bool inside = true;
             int lcell = 0;
             if (has) {
@@ -486,19 +449,25 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               for (int d = 0; d < DIM; d++) inside &= (seg[k].c[d] >= 0) && (seg[k].c[d] < (d == 0 ? G::TX : (d == 1 ? G::TY : G::TZ)));
               lcell = linear_cell<DIM>(seg[k].c);
             }
-            const unsigned hm = __ballot_sync(FULL, has);
             const unsigned im = __ballot_sync(FULL, has && inside);
+            const unsigned om = __ballot_sync(FULL, has && !inside);
+            int hb = 0;
+            if (om) {  // (warp-uniform) reserve room in the CTA's halo list
+              if (lane == 0) hb = atomicAdd(&s_nh, __popc(om));
+              hb = __shfl_sync(FULL, hb, 0);
+            }
             if (has) {
-              const int e = inside ? nlo + __popc(im & lt_mask) : xcap - 1 - (nhi + __popc((hm & ~im) & lt_mask));
-              const bool fits = P::FAST && (inside ? e < xcap_lo : e >= xcap_lo);
-              if (fits) {
+              const int e = inside ? nlo + __popc(im & lt_mask) : hb + __popc(om & lt_mask);
+              if (inside ? e < xcap : e < P::HCAP) {
+                T *dl = inside ? xl : hl;
+                const int st = inside ? xcap : P::HCAP;
 #pragma unroll
                 for (int d = 0; d < DIM; d++) {
-                  xl[d * xcap + e] = seg[k].p0[d];
-                  xl[(DIM + d) * xcap + e] = seg[k].p1[d];
+                  dl[d * st + e] = seg[k].p0[d];
+                  dl[(DIM + d) * st + e] = seg[k].p1[d];
                 }
-                xl[2 * DIM * xcap + e] = q;
-                if (DIM == 2) xl[(2 * DIM + 1) * xcap + e] = seg[k].vz;
+                dl[(DIM + 3) * st + e] = q;
+                if (DIM == 2) dl[(DIM + 2) * st + e] = seg[k].vz;
                 int link;
                 if (inside) {
                   link = atomicExch(&heads[lcell], ((wid << 12) | e) + 1);  // push on the cell's list
@@ -507,118 +476,250 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
 #pragma unroll
                   for (int d = 0; d < DIM; d++) link |= (seg[k].c[d] + 1) << (5 * d);
                 }
-                xl[P::DW * xcap + e] = (T)link;
+                dl[NC * st + e] = (T)link;
               } else {
                 direct |= 1u << k;
               }
             }
             nlo += __popc(im);
-            nhi += __popc(hm & ~im);
           }
           if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
+          __syncwarp();
+        };
+
+        // -- 1. push, 32 particles per warp and round ------------------------------------------
+        int ncell_ = 0;
+        if (32 * wid + lane < tot) ncell_ = a.spc.cell[off + qa + 32 * wid + lane];
+        T *sc = a.scc.base + a.scc.blk(so + qa + 32 * wid + lane);  // this lane's scratch slot, round 0
+        for (int r = 0;; r++, sc += NTHREADS / 32 * P::CHUNK_WORDS) {
+          const bool done = r >= nrounds;  // (uniform) one more trip for what is left in the queue
+          bool cross = false;
+          int lc_old = 0;
+          const int m = r * NTHREADS + 32 * wid + lane;
+          const bool active = !done && m < tot, parked = m < np;
+          if (!done) {
+          const int cell = ncell_;
+          if (m + NTHREADS < tot) ncell_ = a.spc.cell[off + qa + m + NTHREADS];
+          T x[DIM], u[3], q = T(0);
+          T *pb_ = buf + P::slot(m);
+          if constexpr (P::FAST) {
+            mbar_wait(&mbar_p[r], (pph >> r) & 1u);
+            if (active) {
+#pragma unroll
+              for (int d = 0; d < DIM; d++) x[d] = pb_[32 * d];
+#pragma unroll
+              for (int d = 0; d < 3; d++) u[d] = pb_[32 * (DIM + d)];
+              q = pb_[32 * (DIM + 3)];
+            }
+          } else {
+            if (active) {
+              const T *gp = a.spc.base + a.spc.blk(off + qa + m);
+#pragma unroll
+              for (int d = 0; d < DIM; d++) x[d] = gp[32 * d];
+#pragma unroll
+              for (int d = 0; d < 3; d++) u[d] = gp[32 * (DIM + d)];
+              q = gp[32 * (DIM + 3)];
+            }
+          }
+          if (active) {
+            int l[DIM], di[3] = {0, 0, 0};
+#pragma unroll
+            for (int d = 0; d < DIM; d++) l[d] = cell_l(cell, d);
+            lc_old = linear_cell<DIM>(l);
+            Seg<DIM, T> seg[DIM + 1];  // (only the direct path keeps the pieces here)
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+              seg[0].p0[d] = x[d];
+              seg[0].c[d] = l[d];
+            }
+            T vz = T(0);
+            const T en = push_move<DIM, ORDER, T>(x, u, l, eb, a.k, seg[0].p1, di, &vz);
+            ene_t = fmadd(q, en, ene_t);
+            bool moved = false;
+            int ncell = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+              moved |= (l[d] < 0) || (l[d] >= tlim[d]);
+              ncell |= (l[d] + 1) << (d * CELL_BITS);
+              cross |= di[d] != 0;
+            }
+            if (DIM == 2) ncell |= 1 << (2 * CELL_BITS);
+            int rank = 0;
+            if (moved) ncell |= CELL_DEAD;
+            else rank = atomicAdd(&hist[linear_cell<DIM>(l)], 1);
+#pragma unroll
+            for (int d = 0; d < DIM; d++) sc[32 * d] = x[d];
+#pragma unroll
+            for (int d = 0; d < 3; d++) sc[32 * (DIM + d)] = u[d];
+            sc[32 * (DIM + 3)] = q;
+            const long long rs = so + qa + m;
+            a.scc.cell[rs] = ncell;
+            a.scr_rank[rs] = rank;
+            if (a.spc.tag) a.scc.tag[rs] = a.spc.tag[off + qa + m];
+            if constexpr (P::FAST) {
+              // park the end point of the trajectory (old cell's frame) where the momentum was
+#pragma unroll
+              for (int d = 0; d < DIM; d++) pb_[32 * (DIM + d)] = seg[0].p1[d];
+              if (DIM == 2) pb_[32 * (DIM + 2)] = vz;
+              cross |= !parked;
+            } else {
+              if (DIM == 2) seg[0].vz = vz;
+              const int nseg = split_trajectory<DIM, T>(seg, di);
+              deposit_segments<DIM, ORDER, T>(seg, nseg, 0xfu, q, jt, a.k, atomic_add);
+            }
+          }
+          }  // !done
+          if constexpr (P::FAST) {
+            // trajectories that leave their cell (and every tail particle) are queued and split
+            // 32 at a time
+            const unsigned qm = __ballot_sync(FULL, cross);
+            if (cross) queue[ncq + __popc(qm & lt_mask)] = m | (lc_old << 12) | (parked ? 0 : 1 << 20);
+            ncq += __popc(qm);
+            if (ncq >= 32 || (done && ncq > 0)) {
+              const int take = min(ncq, 32);
+              split_queued(ncq - take, take);
+              ncq -= take;
+            }
+          }
+          if (done) break;
+        }
+        if constexpr (P::FAST) pph ^= (1u << nrounds) - 1u;
+
+        __syncthreads();  // every warp's trajectories and lists are complete
+
+        if (!more) {
+          // all particles of the tile are pushed: new-cell histogram -> cell offsets of the sorted
+          // tile, room for the leavers in the mover buffer.  Done here, before the deposit, so that
+          // every warp can go on to the sort as soon as its own cells are deposited.
+          const int start = block_scan(hist[tid], &nlive, s_warp);
+          hist[tid] = start;  // counts -> offsets
+          if (tid == 0) {
+            const int nmov = n - nlive;
+            int b = 0;
+            if (nmov > 0) {
+              b = atomicAdd(a.mv.count, nmov);
+              if (b + nmov > a.mv.cap) {
+                atomicOr(a.errflag, ERRF_MOVER_OVERFLOW);
+                b = -1;
+              }
+            }
+            s_base = b;
+            a.tile_cnt[tile] = nlive;
+            a.tile_nsorted[tile] = nlive;
+          }
+          int *g_cs = a.cell_start + (size_t)tile * (G::NCELL + 1);
+          g_cs[tid] = start;
+          if (tid == 0) g_cs[G::NCELL] = nlive;
+          __syncthreads();  // offsets and s_base visible to the sort
         }
 
-        __syncthreads();  // every warp's parked trajectories and lists are complete
-
         if constexpr (P::FAST) {
-          // -- 2. deposit: one lane per (cell, part) walks the cell's parked trajectories and its
-          // list of foreign pieces; the whole stencil is accumulated in registers -------------
-          const int mya = max(cs[c_lo + lane], pa), myb = min(cs[c_lo + lane + 1], pb);
-          const unsigned cm = __ballot_sync(FULL, (np > 0 && mya < myb) || heads[c_lo + lane] != 0);
-          if (cm) {
-            const int first = __ffs(cm) - 1;
-            const int ncp = 32 - __clz(cm) - first;
-            int parts = 1;
-            while (parts * 2 * ncp <= 32) parts *= 2;
-            const bool on = lane < ncp * parts;
-            const int cl = first + lane % ncp, part = lane / ncp;
-            const int c = c_lo + cl;
-            const int ia = (on && np > 0) ? max(cs[c], pa) + part : 0, ib = (on && np > 0) ? min(cs[c + 1], pb) : 0;
+          // -- 2. deposit: one lane per cell walks the cell's trajectories and its list of foreign
+          // pieces; the whole stencil is accumulated in registers and flushed once.  The cells are
+          // dealt to the lanes in the order of their particle counts, so the 32 lanes of a warp
+          // have (almost) the same number of trajectories to walk.
+          int *bucket = cs2 + (cur ^ 1) * P::CS_STRIDE;  // (the next tile's offsets are stored at the tile's end)
+          unsigned char *order = reinterpret_cast<unsigned char *>(bucket + 64);
+          if (tid < 64) bucket[tid] = 0;
+          __syncthreads();
+          int cnt_own = (np > 0) ? max(0, min(cs[tid + 1], pb) - max(cs[tid], pa)) : 0;
+          if (heads[tid] != 0) cnt_own++;
+          const int bk = 63 - min(cnt_own, 63);  // fullest cells first
+          const int r_in = atomicAdd(&bucket[bk], 1);
+          __syncthreads();
+          int btot;
+          const int bbase = block_scan(tid < 64 ? bucket[tid] : 0, &btot, s_warp);
+          __syncthreads();
+          if (tid < 64) bucket[tid] = bbase;
+          __syncthreads();
+          order[bucket[bk] + r_in] = (unsigned char)tid;
+          __syncthreads();
+          const int c = order[tid];
+          int i = (np > 0) ? max(cs[c], pa) : 0;
+          const int ib = (np > 0) ? min(cs[c + 1], pb) : 0;
+          int id = heads[c];
+          if (id) heads[c] = 0;
+          if (i < ib || id) {
             T acc[P::NACC];
 #pragma unroll
             for (int k = 0; k < P::NACC; k++) acc[k] = T(0);
-            const auto accumulate = [&](const Seg<DIM, T> &sg, T q) {
+            while (i < ib || id) {
+              const T *src;
+              int st;
+              if (i < ib) {  // a trajectory parked in its staged slot
+                src = buf + P::slot(i - pa);
+                st = 32;
+                i++;
+              } else {       // a listed piece
+                const int w = (id - 1) >> 12, e = (id - 1) & 4095;
+                src = buf + s_xl[w] + e;
+                st = s_xcap[w];
+                id = (int)src[NC * st];
+              }
+              Seg<DIM, T> sg;
+#pragma unroll
+              for (int d = 0; d < DIM; d++) {
+                sg.p0[d] = src[d * st];
+                sg.p1[d] = src[(DIM + d) * st];
+              }
+              const T q = src[(DIM + 3) * st];
+              if (DIM == 2) sg.vz = src[(DIM + 2) * st];
               segment_current<DIM, ORDER, T>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
                 T &r = acc[P::acc_index(comp, k1, k2, k3)];
                 r = fmadd(f1, f2, r);
               });
-            };
-            for (int i = ia; i < ib; i += parts) {
-              const int j = i - pa;
-              Seg<DIM, T> sg;
-#pragma unroll
-              for (int d = 0; d < DIM; d++) {
-                sg.p0[d] = wbuf[d * tot + j];
-                sg.p1[d] = wbuf[(DIM + d) * tot + j];
-              }
-              const T q = wbuf[2 * DIM * tot + j];
-              if (DIM == 2) sg.vz = wbuf[(2 * DIM + 1) * tot + j];
-              accumulate(sg, q);
-            }
-            int id = (on && part == 0) ? heads[c] : 0;
-            if (on && part == 0 && id) heads[c] = 0;
-            bool any = ia < ib;
-            while (id) {
-              any = true;
-              const int w = (id - 1) >> 12, e = (id - 1) & 4095;
-              const T *xe = buf + s_xl[w] + e;
-              const int st = s_xcap[w];
-              Seg<DIM, T> sg;
-#pragma unroll
-              for (int d = 0; d < DIM; d++) {
-                sg.p0[d] = xe[d * st];
-                sg.p1[d] = xe[(DIM + d) * st];
-              }
-              const T q = xe[2 * DIM * st];
-              if (DIM == 2) sg.vz = xe[(2 * DIM + 1) * st];
-              id = (int)xe[P::DW * st];
-              accumulate(sg, q);
             }
             int lc[3];
             lc[0] = c % G::TX;
             lc[1] = (c / G::TX) % G::TY;
             lc[2] = c / (G::TX * G::TY);
             T *pj = jt + jtile_base<DIM, ORDER, T>(lc);
-            if (ncp == 32) {
-              // lanes are consecutive cells along x: neighbours add up the stencil columns they
-              // share with warp shuffles; one shared atomic per grid point of the row instead of
-              // one per cell and point
-              flush_merged<DIM, ORDER, T, P>(acc, pj, lc[0]);
-            } else if (any) {
-              for_each_stencil_entry<DIM, ORDER>([&](int comp, int k1, int k2, int k3) {
-                atomicAdd(pj + comp * G::JVOL + k1 + G::JX * (k2 + G::JY * k3),
-                          acc[P::acc_index(comp, k1, k2, k3)]);
-              });
-            }
+            flush_stencil<DIM, ORDER, T, P>(acc, pj);
           }
+        }
+        if constexpr (P::FAST) {
           // -- 3. pieces in halo cells (owned by a neighbouring tile): straight into the J tile --
-          for (int e = xcap - 1 - lane; e >= max(xcap - nhi, xcap_lo); e -= 32) {
+          const int nh = min(s_nh, P::HCAP);
+          for (int e = tid; e < nh; e += NTHREADS) {
             Seg<DIM, T> sg;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
-              sg.p0[d] = xl[d * xcap + e];
-              sg.p1[d] = xl[(DIM + d) * xcap + e];
+              sg.p0[d] = hl[d * P::HCAP + e];
+              sg.p1[d] = hl[(DIM + d) * P::HCAP + e];
             }
-            const T q = xl[2 * DIM * xcap + e];
-            if (DIM == 2) sg.vz = xl[(2 * DIM + 1) * xcap + e];
-            const int pc = (int)xl[P::DW * xcap + e];
+            const T q = hl[(DIM + 3) * P::HCAP + e];
+            if (DIM == 2) sg.vz = hl[(DIM + 2) * P::HCAP + e];
+            const int pc = (int)hl[NC * P::HCAP + e];
 #pragma unroll
             for (int d = 0; d < DIM; d++) sg.c[d] = ((pc >> (5 * d)) & 31) - 1;
             deposit_segment<DIM, ORDER, T>(sg, q, jt, a.k, atomic_add);
           }
         }
-        if (more) __syncthreads();  // the next piece reuses the buffers other warps may still read
         qa = qb;
+        if (more) {
+          __syncthreads();  // the next piece reuses the buffer
+          if (tid == 0) s_nh = 0;
+          if (P::FAST && tid == 32) stage_particles(off + qa, min(n - qa, P::TCAP));
+          __syncthreads();  // (halo list counter reset before the next piece adds to it)
+        }
       } while (more);
     }
     ene += (double)ene_t;
     ene_t = T(0);
-    __syncthreads();  // J tile, histogram and scratch complete; E/B tile and cs free
 
-    // ---- 4. J tile -> HBM; the next tile's E/B loads start ----------------------------------
-    tile_origin(tile, o0);  // (recomputed: not kept in registers through the push)
-    if constexpr (P::TMA_J) {
-      if (tid == 0) {
+    // ---- 4. the last warp to finish its deposit sends the J tile to HBM and starts the next
+    // tile's loads; nobody waits: the other warps are already sorting ---------------------------
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence_block();  // this warp's J-tile updates and buffer reads before the arrival
+      last = atomicAdd(&s_arrive, 1) == NTHREADS / 32 - 1;
+    }
+    if (last) {  // (one thread of the CTA)
+      __threadfence_block();
+      s_arrive = 0;
+      tile_origin(tile, o0);  // (recomputed: not kept in registers through the push)
+      if constexpr (P::TMA_J) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // atomics -> visible to TMA
         const int c0 = o0[0] + a.g.gl[0] + G::HALO_LO;
         const int c1 = o0[1] + a.g.gl[1] + G::HALO_LO;
@@ -630,7 +731,89 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-    } else {
+      if (s_next[0] < a.tl.ntile) {
+        stage_fields(s_next[0]);
+        if (P::FAST) stage_particles(s_next_off, min(s_next[1], P::TCAP));
+      }
+    }
+
+    // ---- 5. sort by new cell: scratch -> particle buffer, leavers -> movers -----------------
+    const int base = s_base;
+    // cell offsets of the CTA's next tile: loaded now, stored below
+    int pre = 0, pre_last = 0;
+    const bool pre_on = P::FAST && s_next[0] < a.tl.ntile && s_next[2] > 0;
+    if (pre_on) {
+      const int *g_cs = a.cell_start + (size_t)s_next[0] * (G::NCELL + 1);
+      pre = g_cs[tid];
+      if (tid == 0) pre_last = g_cs[G::NCELL];
+    }
+    // The warps take runs of PB * 32 particles from a counter (a warp that finished its deposit
+    // early sorts more); PB particles per thread in flight: the scratch range sits in L2, latency
+    // is what costs.
+    constexpr int PB = 2;
+    const T *scr0 = a.scc.base + (so >> 5) * P::CHUNK_WORDS + lane;
+    T *dstb = a.spc.base + (off >> 5) * P::CHUNK_WORDS;
+    for (;;) {
+      int i0 = 0;
+      if (lane == 0) i0 = atomicAdd(&s_sortc, PB * 32);
+      i0 = __shfl_sync(0xffffffffu, i0, 0);
+      if (i0 >= n) break;
+      int cellv[PB], dst[PB];
+      T vx[PB][DIM], vp[PB][3], vq[PB];
+      long long vt[PB];
+#pragma unroll
+      for (int k = 0; k < PB; k++) {
+        const int i = i0 + 32 * k + lane;
+        cellv[k] = 0;
+        dst[k] = 0;
+        vt[k] = 0;
+        if (i < n) {
+          cellv[k] = a.scc.cell[so + i];
+          dst[k] = a.scr_rank[so + i];
+          if (a.spc.tag) vt[k] = a.scc.tag[so + i];
+          const T *sp_ = scr0 + (size_t)((i0 >> 5) + k) * P::CHUNK_WORDS;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) vx[k][d] = sp_[32 * d];
+#pragma unroll
+          for (int d = 0; d < 3; d++) vp[k][d] = sp_[32 * (DIM + d)];
+          vq[k] = sp_[32 * (DIM + 3)];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PB; k++) {
+        const int i = i0 + 32 * k + lane;
+        if (i >= n) continue;
+        if (cellv[k] < 0) {
+          if (base < 0) continue;  // mover buffer overflow: reported through errflag
+          const int m = base + atomicAdd(&s_mcnt, 1);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {
+            a.mvc.base[d * a.mvc.stride + m] = vx[k][d];
+            a.mvc.cell[d * a.mvc.stride + m] = o0[d] + cell_l(cellv[k] & ~CELL_DEAD, d) + 1;
+          }
+#pragma unroll
+          for (int d = 0; d < 3; d++) a.mvc.base[(DIM + d) * a.mvc.stride + m] = vp[k][d];
+          a.mvc.base[(DIM + 3) * a.mvc.stride + m] = vq[k];
+          if (a.spc.tag) a.mvc.tag[m] = vt[k];
+        } else {
+          int l[DIM];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) l[d] = cell_l(cellv[k], d);
+          const int s = hist[linear_cell<DIM>(l)] + dst[k];  // slot inside the tile
+          T *dp = dstb + P::slot(s);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) dp[32 * d] = vx[k][d];
+#pragma unroll
+          for (int d = 0; d < 3; d++) dp[32 * (DIM + d)] = vp[k][d];
+          dp[32 * (DIM + 3)] = vq[k];
+          a.spc.cell[off + s] = cellv[k];
+          if (a.spc.tag) a.spc.tag[off + s] = vt[k];
+        }
+      }
+    }
+    if (P::TMA_J && last) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();  // sort done (offsets in hist free), every warp's deposit done, J tile read by the TMA
+    if constexpr (!P::TMA_J) {
       for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) {
         const T v = jt[i];
         if (v != T(0)) {
@@ -645,144 +828,23 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           if (q0 >= 0 && q0 < a.g.S[0] && q1 >= 0 && q1 < a.g.S[1] && q2 >= 0 && q2 < a.g.S[2])
             atomicAdd(&a.J[c][a.g.at(q0, q1, q2)], v);
         }
+        jt[i] = T(0);
       }
+    } else {
+      for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
     }
-    if (tid == 32) {
-      s_tile = s_next[0]; s_n = s_next[1]; s_ns = s_next[2]; s_off = s_next_off;
-      if (s_next[0] < a.tl.ntile) stage_fields(s_next[0]);
-    }
-
-    // ---- 5. sort by new cell: scratch -> particle buffer, leavers -> movers -----------------
-    int nlive;
-    const int start = block_scan(hist[tid], &nlive, s_warp);
-    hist[tid] = start;  // counts -> offsets
-    const int nmov = n - nlive;
-    if (tid == 0) {
-      int b = 0;
-      if (nmov > 0) {
-        b = atomicAdd(a.mv.count, nmov);
-        if (b + nmov > a.mv.cap) {
-          atomicOr(a.errflag, ERRF_MOVER_OVERFLOW);
-          b = -1;
-        }
-      }
-      s_base = b;
-      a.tile_cnt[tile] = nlive;
-      a.tile_nsorted[tile] = nlive;
-    }
-    {
-      int *g_cs = a.cell_start + (size_t)tile * (G::NCELL + 1);
-      g_cs[tid] = start;
-      if (tid == 0) g_cs[G::NCELL] = nlive;
-    }
-    __syncthreads();
-    const int base = s_base;
-    // cell offsets of the CTA's next tile (published by thread 32 above): loaded now, stored below
-    int pre = 0, pre_last = 0;
-    const bool pre_on = P::FAST && s_tile < a.tl.ntile && s_ns > 0;
-    if (pre_on) {
-      const int *g_cs = a.cell_start + (size_t)s_tile * (G::NCELL + 1);
-      pre = g_cs[tid];
-      if (tid == 0) pre_last = g_cs[G::NCELL];
-    }
-    // PB particles per thread in flight: the scratch range sits in L2, latency is what costs
-    tile_origin(tile, o0);
-    constexpr int PB = 2;
-#pragma unroll 1
-    for (int i0 = 0; i0 < n; i0 += PB * NTHREADS) {
-      int cellv[PB], dst[PB];  // dst: slot in the particle buffer, or ~slot in the mover buffer
-      T vx[PB][DIM], vp[PB][3], vq[PB];
-#pragma unroll
-      for (int k = 0; k < PB; k++) {
-        const int i = i0 + tid + k * NTHREADS;
-        cellv[k] = 0;
-        dst[k] = 0;
-        if (i < n) {
-          cellv[k] = a.scc.cell[so + i];
-          dst[k] = a.scc.cell[a.scc.stride + so + i];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < PB; k++) {
-        const int i = i0 + tid + k * NTHREADS;
-        if (i < n) {
-          const long long r = so + i;
-#pragma unroll
-          for (int d = 0; d < DIM; d++) vx[k][d] = a.scc.base[d * a.scc.stride + r];
-#pragma unroll
-          for (int d = 0; d < 3; d++) vp[k][d] = a.scc.base[(DIM + d) * a.scc.stride + r];
-          vq[k] = a.scc.base[(DIM + 3) * a.scc.stride + r];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < PB; k++) {
-        const int i = i0 + tid + k * NTHREADS;
-        if (i >= n) continue;
-        if (cellv[k] < 0) {
-          if (base < 0) continue;  // mover buffer overflow: reported through errflag
-          const int m = base + atomicAdd(&s_mcnt, 1);
-          if (a.spc.tag) a.scc.cell[a.scc.stride + so + i] = m;  // the tag pass below follows
-#pragma unroll
-          for (int d = 0; d < DIM; d++) {
-            a.mvc.base[d * a.mvc.stride + m] = vx[k][d];
-            a.mvc.cell[d * a.mvc.stride + m] = o0[d] + cell_l(cellv[k] & ~CELL_DEAD, d) + 1;
-          }
-#pragma unroll
-          for (int d = 0; d < 3; d++) a.mvc.base[(DIM + d) * a.mvc.stride + m] = vp[k][d];
-          a.mvc.base[(DIM + 3) * a.mvc.stride + m] = vq[k];
-        } else {
-          int l[DIM];
-#pragma unroll
-          for (int d = 0; d < DIM; d++) l[d] = cell_l(cellv[k], d);
-          const long long s = off + hist[linear_cell<DIM>(l)] + dst[k];
-#pragma unroll
-          for (int d = 0; d < DIM; d++) a.spc.base[d * a.spc.stride + s] = vx[k][d];
-#pragma unroll
-          for (int d = 0; d < 3; d++) a.spc.base[(DIM + d) * a.spc.stride + s] = vp[k][d];
-          a.spc.base[(DIM + 3) * a.spc.stride + s] = vq[k];
-          a.spc.cell[s] = cellv[k];
-        }
-      }
-    }
-    if (a.spc.tag) {  // species{add_tag}: the tags follow their particles
-#pragma unroll 1
-      for (int i0 = 0; i0 < n; i0 += PB * NTHREADS) {
-        int cellv[PB], rk[PB];
-        long long vt[PB];
-#pragma unroll
-        for (int k = 0; k < PB; k++) {
-          const int i = i0 + tid + k * NTHREADS;
-          if (i < n) {
-            cellv[k] = a.scc.cell[so + i];
-            rk[k] = a.scc.cell[a.scc.stride + so + i];
-            vt[k] = a.scc.tag[so + i];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < PB; k++) {
-          const int i = i0 + tid + k * NTHREADS;
-          if (i >= n) continue;
-          if (cellv[k] < 0) {
-            if (base >= 0) a.mvc.tag[rk[k]] = vt[k];
-          } else {
-            int l[DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; d++) l[d] = cell_l(cellv[k], d);
-            a.spc.tag[off + hist[linear_cell<DIM>(l)] + rk[k]] = vt[k];
-          }
-        }
-      }
-    }
+    hist[tid] = 0;
     if (pre_on) {
       int *cs_next = cs2 + (cur ^ 1) * P::CS_STRIDE;
       cs_next[tid] = pre;
       if (tid == 0) cs_next[G::NCELL] = pre_last;
     }
-    if (P::TMA_J && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncthreads();  // sort done (offsets in hist free), J tile read by the TMA
-    for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
-    hist[tid] = 0;
-    if (tid == 0) s_mcnt = 0;
+    if (tid == 0) {
+      s_mcnt = 0;
+      s_nh = 0;
+      s_sortc = 0;
+      s_tile = s_next[0]; s_n = s_next[1]; s_ns = s_next[2]; s_off = s_next_off;
+    }
     cur ^= 1;
   }
 

@@ -12,10 +12,9 @@ struct alignas(64) TmaMaps {
   CUtensorMap m[9];
 };
 
-// SoA columns at a constant stride, as the kernel addresses them (one base pointer per buffer):
-// real column c of slot s is base[c * stride + s] -- x(D), p(3), q in this order; `cell` is the first
-// int column behind them (species / scratch: packed cell, scratch: + rank one stride further;
-// movers: ix(D)); `tag` is null when the species carries no tags
+// SoA columns at a constant stride (the mover buffer as the kernel addresses it): real column c of
+// slot s is base[c * stride + s] -- x(D), p(3), q in this order; `cell` is the first int column
+// behind them (ix(D)); `tag` is null when the species carries no tags
 template <typename T> struct Cols {
   T *base;
   long long stride;
@@ -24,13 +23,16 @@ template <typename T> struct Cols {
 };
 
 template <typename T> struct PushArgs {
-  Cols<T> spc, scc, mvc;  // species buffer, per-CTA scratch ranges, mover buffer
-  MoverView<T> mv;        // (count, cap)
+  SpeciesView<T> spc;   // species buffer
+  SpeciesView<T> scc;   // per-CTA scratch ranges: new state in the old order (cell = new packed cell)
+  int *scr_rank;        // scratch: rank of the particle inside its new cell
+  Cols<T> mvc;          // mover buffer
+  MoverView<T> mv;      // (count, cap)
   const int *tile_off;
   int *tile_cnt;
   int *tile_nsorted;    // the first tile_nsorted[t] particles of tile t are sorted by cell
   int *cell_start;      // [ntile][TILE_NCELL + 1] offsets of the cells inside the sorted range
-  int scr_stride;
+  int scr_stride;       // slots per CTA scratch range (multiple of 32)
   int *tile_counter;    // persistent CTAs take tiles from here (zeroed before the launch)
   T *J[3];
   Grid g;

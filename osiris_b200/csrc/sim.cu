@@ -249,15 +249,12 @@ template <typename T> struct Sim final : SimBase {
   // the push kernel's scratch)
   static size_t slot_bytes(int dim) { return (dim + 4) * sizeof(T) + 2 * sizeof(int) + sizeof(long long); }
   static size_t species_bytes(int dim, long long cap) { return (size_t)cap * slot_bytes(dim); }
+  // cap is a multiple of 32 slots: the real columns are blocked by 32 (common.cuh: SpeciesView)
   void carve(void *mem, int dim, long long cap, SpeciesView<T> *v) const {
     char *p = (char *)mem;
     v->tag = cfg.no_tags ? nullptr : (long long *)p; p += cap * sizeof(long long);
-    for (int d = 0; d < 3; d++) {
-      v->x[d] = nullptr;
-      if (d < dim) { v->x[d] = (T *)p; p += cap * sizeof(T); }
-    }
-    for (int d = 0; d < 3; d++) { v->p[d] = (T *)p; p += cap * sizeof(T); }
-    v->q = (T *)p; p += cap * sizeof(T);
+    v->nc = dim + 4;
+    v->base = (T *)p; p += cap * (dim + 4) * sizeof(T);
     v->cell = (int *)p;
   }
   int species_create(int id, double rqm, long long np_max) override {
@@ -547,8 +544,7 @@ template <typename T> struct Sim final : SimBase {
       if (!s.created) continue;
       if (s.movers_pending) { set_error("advance_deposit called twice without particles_update_boundary"); return OSGPU_ERR_INVALID; }
       PushArgs<T> a;
-      const SpeciesView<T> &cv = s.v[s.cur];
-      a.spc.base = cv.x[0]; a.spc.stride = s.cap; a.spc.cell = cv.cell; a.spc.tag = cv.tag;
+      a.spc = s.v[s.cur];
       a.mv = s.mv;
       a.mvc.base = s.mv.x[0]; a.mvc.stride = s.mv.cap; a.mvc.cell = s.mv.ix[0]; a.mvc.tag = s.mv.tag;
       a.tile_off = s.tile_off[s.cur];
@@ -559,10 +555,9 @@ template <typename T> struct Sim final : SimBase {
       // persistent CTAs; each owns one scratch range (widest tile) carved from the idle buffer
       int nblocks = std::min(tl.ntile, n_sm * push_bps);
       while (nblocks > 1 && (long long)nblocks * s.max_range > s.cap) nblocks--;
-      const long long nscr = std::max<long long>((long long)nblocks * s.max_range, 1);
-      SpeciesView<T> sv;
-      carve(s.mem[1 - s.cur], dim, nscr, &sv);
-      a.scc.base = sv.x[0]; a.scc.stride = nscr; a.scc.cell = sv.cell; a.scc.tag = sv.tag;  // rank: cell + stride
+      const long long nscr = std::max<long long>((long long)nblocks * s.max_range, 32);
+      carve(s.mem[1 - s.cur], dim, nscr, &a.scc);
+      a.scr_rank = a.scc.cell + nscr;
       a.scr_stride = s.max_range;
       OSGPU_CUDA(cudaMemsetAsync(s.tile_counter, 0, sizeof(int), st));
       for (int k = 0; k < 3; k++) a.J[k] = J.c[k];

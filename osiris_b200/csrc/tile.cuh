@@ -6,6 +6,8 @@
 // accumulates the tile's current into a shared-memory J tile (tile + stencil halo + one cell of
 // motion), and writes that back once.
 #pragma once
+#include <utility>
+
 #include "pic_math.cuh"
 
 namespace pic {
@@ -55,15 +57,54 @@ template <typename T> struct PushConst {
   T jnorm[3];   // dx_d / dt / 2 (2D) | 3 (3D)  (:1184-1186, :517-518)
 };
 
+
+// The NP^DIM tile values of one component around a particle, loaded back to back with constant
+// offsets from one address.  On the device the loads are volatile asm statements: the compiler
+// keeps them together ahead of the arithmetic instead of interleaving every load with its use,
+// so the shared-memory latency is paid once per component and not once per line.
+template <int BYTES> struct TileLd;
+template <> struct TileLd<4> {
+  template <int OFF> static PIC_HD float ld(const float *p) {
+#if defined(__CUDA_ARCH__)
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared(p)), "n"(OFF * 4));
+    return v;
+#else
+    return p[OFF];
+#endif
+  }
+};
+template <> struct TileLd<8> {
+  template <int OFF> static PIC_HD double ld(const double *p) {
+#if defined(__CUDA_ARCH__)
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)), "n"(OFF * 8));
+    return v;
+#else
+    return p[OFF];
+#endif
+  }
+};
+template <int DIM, int ORDER, typename T, int... I>
+PIC_HD void tile_block_impl(const T *p, T *v, std::integer_sequence<int, I...>) {
+  using G = Tile<DIM, ORDER, T>;
+  constexpr int NP = G::NP;
+  ((v[I] = TileLd<(int)sizeof(T)>::template ld<(I % NP) + G::EXP * (((I / NP) % NP) + G::EY * (I / (NP * NP)))>(p)), ...);
+}
+template <int DIM, int ORDER, typename T> PIC_HD void tile_block(const T *p, T *v) {
+  constexpr int NP = Tile<DIM, ORDER, T>::NP;
+  tile_block_impl<DIM, ORDER, T>(p, v, std::make_integer_sequence<int, (DIM == 3 ? NP * NP * NP : NP * NP)>{});
+}
+
 // ------------------------------------------------------------------------------------------
-// One particle, first half: interpolate E,B from the tile, Boris, move, trim, split.
-// x[], u[] and l[] are advanced in place; l[] may leave [0,T) by one cell.  seg[0..nseg) are
-// the trajectory pieces (each inside one cell); returns u^2/(gamma+1) of the centred momentum.
+// One particle, first half: interpolate E,B from the tile, Boris, move, trim.
+// x[], u[] and l[] are advanced in place; l[] may leave [0,T) by one cell.  x1[] is the new position
+// still in the old cell's frame (untrimmed), di[] the cell change, *vz (2D) the out-of-plane velocity;
+// returns u^2/(gamma+1) of the centred momentum.
 // Statement order follows ADVANCE_DEPOSIT_2D/3D (simd/os-spec-push-avx2.c:471-760, 1141-1472).
 // ------------------------------------------------------------------------------------------
 template <int DIM, int ORDER, typename T>
-PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DIM, T> *seg,
-                  int *nseg_out) {
+PIC_HD T push_move(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, T *x1, int *di, T *vz) {
   using G = Tile<DIM, ORDER, T>;
   constexpr int NP = G::NP;
   T w[DIM][NP], wh[DIM][NP];
@@ -85,12 +126,14 @@ PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DI
       const bool hy = (c == 1) || (c == 3) || (c == 5);
       const T *wx = hx ? wh[0] : w[0], *wy = hy ? wh[1] : w[1];
       const T *p = eb + c * G::ESTRIDE + (hx ? bh[0] : b0[0]) + G::EXP * (hy ? bh[1] : b0[1]);
+      T v[NP * NP];
+      tile_block<DIM, ORDER, T>(p, v);
       T acc = T(0.0);
 #pragma unroll
       for (int k2 = 0; k2 < NP; k2++) {
         T line = T(0.0);
 #pragma unroll
-        for (int k1 = 0; k1 < NP; k1++) line = fmadd(p[k1 + G::EXP * k2], wx[k1], line);
+        for (int k1 = 0; k1 < NP; k1++) line = fmadd(v[k1 + NP * k2], wx[k1], line);
         acc = fmadd(line, wy[k2], acc);
       }
       f[c] = acc;
@@ -105,6 +148,8 @@ PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DI
       const T *wx = hx ? wh[0] : w[0], *wy = hy ? wh[1] : w[1], *wz = hz ? wh[DIM - 1] : w[DIM - 1];
       const T *p = eb + c * G::ESTRIDE + (hx ? bh[0] : b0[0]) +
                    G::EXP * ((hy ? bh[1] : b0[1]) + G::EY * (hz ? bh[DIM - 1] : b0[DIM - 1]));
+      T v[NP * NP * NP];
+      tile_block<DIM, ORDER, T>(p, v);
       T acc = T(0.0);
 #pragma unroll
       for (int k3 = 0; k3 < NP; k3++) {
@@ -114,7 +159,7 @@ PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DI
           T line = T(0.0);
 #pragma unroll
           for (int k1 = 0; k1 < NP; k1++)
-            line = fmadd(p[k1 + G::EXP * (k2 + G::EY * k3)], wx[k1], line);
+            line = fmadd(v[k1 + NP * (k2 + NP * k3)], wx[k1], line);
           plane = fmadd(line, wy[k2], plane);
         }
         acc = fmadd(plane, wz[k3], acc);
@@ -124,24 +169,38 @@ PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DI
   }
   const T ene = boris<T>(k.tem, f[0], f[1], f[2], f[3], f[4], f[5], u);
   const T rg = rgamma<T>(u);
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    x1[d] = fmadd(u[d] * rg, k.dt_dx[d], x[d]);
+    di[d] = ntrim<T>(x1[d]);
+    x[d] = x1[d] - T(di[d]);
+    l[d] += di[d];
+  }
+  if constexpr (DIM == 2) *vz = u[2] * rg;
+  return ene;
+}
 
+// Split a trajectory (seg[0]: p0, untrimmed p1, cell c, 2D vz) at the cell faces it crosses
+// (simd/split-vec.h); di[] = ntrim(p1).  Returns the number of pieces.
+template <int DIM, typename T> PIC_HD int split_trajectory(Seg<DIM, T> *seg, const int *di) {
+  if constexpr (DIM == 2) return split2d<T>(seg, di[0], di[1]);
+  else return split3d<T>(seg, di);
+}
+
+// push_move + split: seg[0..nseg) are the trajectory pieces (each inside one cell).
+template <int DIM, int ORDER, typename T>
+PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DIM, T> *seg,
+                  int *nseg_out) {
   int di[3] = {0, 0, 0};
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
-    const T x1 = fmadd(u[d] * rg, k.dt_dx[d], x[d]);
-    di[d] = ntrim<T>(x1);
     seg[0].p0[d] = x[d];
-    seg[0].p1[d] = x1;
     seg[0].c[d] = l[d];
-    x[d] = x1 - T(di[d]);
-    l[d] += di[d];
   }
-  if constexpr (DIM == 2) {
-    seg[0].vz = u[2] * rg;
-    *nseg_out = split2d<T>(seg, di[0], di[1]);
-  } else {
-    *nseg_out = split3d<T>(seg, di);
-  }
+  T vz = T(0);
+  const T ene = push_move<DIM, ORDER, T>(x, u, l, eb, k, seg[0].p1, di, &vz);
+  if constexpr (DIM == 2) seg[0].vz = vz;
+  *nseg_out = split_trajectory<DIM, T>(seg, di);
   return ene;
 }
 

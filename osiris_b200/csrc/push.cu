@@ -244,8 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   int *heads = reinterpret_cast<int *>(smem_raw + P::OFF_HEADS);  // per cell: list of foreign pieces
   __shared__ __align__(8) uint64_t mbar;                 // E/B tile
   __shared__ __align__(8) uint64_t mbar_p[P::NROUND];    // staged particles, one per round of 256
-  __shared__ int s_xl[NTHREADS / 32], s_xcap[NTHREADS / 32];
-  __shared__ int s_tile, s_n, s_ns, s_mcnt, s_base, s_nh, s_arrive, s_sortc;
+  __shared__ int s_tile, s_n, s_ns, s_mcnt, s_base, s_nh, s_nx, s_arrive, s_sortc, s_pushc;
   __shared__ long long s_off, s_next_off;
   __shared__ int s_next[3];
   __shared__ int s_warp[NTHREADS / 32];
@@ -321,6 +320,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_mcnt = 0;
     s_nh = 0;
+    s_nx = 0;
+    s_pushc = 0;
     s_arrive = 0;
     s_sortc = 0;
   }
@@ -390,19 +391,16 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         const int pa = qa, pb = qa + np;                  // sorted particles [pa, pb)
         const int nrounds = (tot + NTHREADS - 1) / NTHREADS;
         more = qb < n;
-        // above the staged particles: per warp a list of trajectory pieces that lie in other cells
-        // of the tile (linked to their cell) and the queue of particles whose trajectory is split
-        const int xbase = NC * ((tot + 31) & ~31);
-        const int wregion = P::FAST ? ((P::BUF_WORDS - P::HCAP * P::XW - xbase) / P::NWARP) & ~3 : 0;
-        const int xcap = P::FAST ? (wregion - P::QWORDS) / P::XW : 0;  // list entries per warp
-        T *xl = buf + xbase + wid * wregion;
-        int *queue = reinterpret_cast<int *>(xl + P::XW * xcap);
+        // above the staged particles: the CTA's pool of trajectory pieces that lie in other cells
+        // of the tile (each linked to its cell), then per warp the queue of particles whose
+        // trajectory is split, and at the top the pieces that lie in halo cells
+        const int nchunks = (tot + 31) >> 5;
+        const int xbase = NC * 32 * nchunks;
+        const int xcap = P::FAST ? (P::BUF_WORDS - P::HCAP * P::XW - P::NWARP * P::QWORDS - xbase) / P::XW : 0;
+        T *xl = buf + xbase;  // SoA with stride xcap
+        int *queue = reinterpret_cast<int *>(buf + P::BUF_WORDS - P::HCAP * P::XW - (P::NWARP - wid) * P::QWORDS);
         T *hl = buf + P::BUF_WORDS - P::HCAP * P::XW;  // halo pieces, SoA with stride HCAP
-        int nlo = 0, ncq = 0;  // warp-uniform: list length, queue length
-        if (P::FAST && lane == 0) {
-          s_xl[wid] = (int)(xl - buf);
-          s_xcap[wid] = xcap;
-        }
+        int ncq = 0;  // (warp-uniform) queue length
 
         // split the queued trajectories [qbase, qbase + cnt) of this warp, one per lane: the piece
         // in the particle's own cell goes back to its staged slot (sorted particles), the others to
@@ -451,13 +449,17 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             }
             const unsigned im = __ballot_sync(FULL, has && inside);
             const unsigned om = __ballot_sync(FULL, has && !inside);
-            int hb = 0;
-            if (om) {  // (warp-uniform) reserve room in the CTA's halo list
+            int xb = 0, hb = 0;
+            if (im) {  // (warp-uniform) reserve room in the CTA's lists
+              if (lane == 0) xb = atomicAdd(&s_nx, __popc(im));
+              xb = __shfl_sync(FULL, xb, 0);
+            }
+            if (om) {
               if (lane == 0) hb = atomicAdd(&s_nh, __popc(om));
               hb = __shfl_sync(FULL, hb, 0);
             }
             if (has) {
-              const int e = inside ? nlo + __popc(im & lt_mask) : hb + __popc(om & lt_mask);
+              const int e = inside ? xb + __popc(im & lt_mask) : hb + __popc(om & lt_mask);
               if (inside ? e < xcap : e < P::HCAP) {
                 T *dl = inside ? xl : hl;
                 const int st = inside ? xcap : P::HCAP;
@@ -470,7 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
                 if (DIM == 2) dl[(DIM + 2) * st + e] = seg[k].vz;
                 int link;
                 if (inside) {
-                  link = atomicExch(&heads[lcell], ((wid << 12) | e) + 1);  // push on the cell's list
+                  link = atomicExch(&heads[lcell], e + 1);  // push on the cell's list
                 } else {
                   link = 0;  // cell coordinates -1..T in 5-bit fields (exact as a float)
 #pragma unroll
@@ -481,25 +483,34 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
                 direct |= 1u << k;
               }
             }
-            nlo += __popc(im);
           }
           if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
           __syncwarp();
         };
 
-        // -- 1. push, 32 particles per warp and round ------------------------------------------
+        // -- 1. push, 32 particles per warp and round; the warps take their rounds from a counter
+        // (the two or three warps that share a scheduler do not advance at the same pace) --------
+        const auto next_round = [&]() {
+          int j = 0;
+          if (lane == 0) j = atomicAdd(&s_pushc, 1);
+          return __shfl_sync(FULL, j, 0);
+        };
+        int j = next_round(), jn = 0;
         int ncell_ = 0;
-        if (32 * wid + lane < tot) ncell_ = a.spc.cell[off + qa + 32 * wid + lane];
-        T *sc = a.scc.base + a.scc.blk(so + qa + 32 * wid + lane);  // this lane's scratch slot, round 0
-        for (int r = 0;; r++, sc += NTHREADS / 32 * P::CHUNK_WORDS) {
-          const bool done = r >= nrounds;  // (uniform) one more trip for what is left in the queue
+        if (32 * j + lane < tot) ncell_ = a.spc.cell[off + qa + 32 * j + lane];
+        T *const sc0 = a.scc.base + ((so + qa) >> 5) * P::CHUNK_WORDS + lane;
+        for (;; j = jn) {
+          const bool done = j >= nchunks;  // (uniform) one more trip for what is left in the queue
           bool cross = false;
           int lc_old = 0;
-          const int m = r * NTHREADS + 32 * wid + lane;
+          const int m = 32 * j + lane;
           const bool active = !done && m < tot, parked = m < np;
           if (!done) {
+          const int r = j >> 3;
+          T *sc = sc0 + (size_t)j * P::CHUNK_WORDS;
           const int cell = ncell_;
-          if (m + NTHREADS < tot) ncell_ = a.spc.cell[off + qa + m + NTHREADS];
+          jn = next_round();
+          if (32 * jn + lane < tot) ncell_ = a.spc.cell[off + qa + 32 * jn + lane];
           T x[DIM], u[3], q = T(0);
           T *pb_ = buf + P::slot(m);
           if constexpr (P::FAST) {
@@ -651,9 +662,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
                 st = 32;
                 i++;
               } else {       // a listed piece
-                const int w = (id - 1) >> 12, e = (id - 1) & 4095;
-                src = buf + s_xl[w] + e;
-                st = s_xcap[w];
+                src = xl + (id - 1);
+                st = xcap;
                 id = (int)src[NC * st];
               }
               Seg<DIM, T> sg;
@@ -698,7 +708,11 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         qa = qb;
         if (more) {
           __syncthreads();  // the next piece reuses the buffer
-          if (tid == 0) s_nh = 0;
+          if (tid == 0) {
+            s_nh = 0;
+            s_nx = 0;
+            s_pushc = 0;
+          }
           if (P::FAST && tid == 32) stage_particles(off + qa, min(n - qa, P::TCAP));
           __syncthreads();  // (halo list counter reset before the next piece adds to it)
         }
@@ -842,6 +856,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     if (tid == 0) {
       s_mcnt = 0;
       s_nh = 0;
+      s_nx = 0;
+      s_pushc = 0;
       s_sortc = 0;
       s_tile = s_next[0]; s_n = s_next[1]; s_ns = s_next[2]; s_off = s_next_off;
     }

@@ -128,12 +128,22 @@ int osgpu_particles_update_boundary(osgpu_sim *sim); /* spec/os-spec-boundary.f0
 int osgpu_sort(osgpu_sim *sim);                      /* spec/os-species.f03:269-332           */
 int osgpu_current_update_boundary(osgpu_sim *sim); /* current/os-current-define.f03:683-727 */
 int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-482 (Yee)   */
+/* Current smoothing.  set_smooth takes what setup_smooth leaves in
+ * t_smooth (vdf/os-vdf-smooth.f90:373-467): order[dim] and scoef[dim][2*max_order+1] in FIELD
+ * precision (real(p_k_fld)), centre tap at index max_order; all orders 0 switches it off.
+ * Needs gc_jay >= (order, order+1) per axis (current/os-current-define.f03:199-205).  Once set,
+ * osgpu_step filters J between jay%update_boundary and emf%advance (os-simulation.f03:654-657);
+ * osgpu_current_smooth is that phase alone = smooth_current (current/os-current-define.f03:298-316)
+ * -> filter_2d/filter_3d (vdf/os-vdf-smooth.f90:639-1105). */
+int osgpu_current_set_smooth(osgpu_sim *sim, const int32_t *order, int max_order, const void *scoef);
+int osgpu_current_smooth(osgpu_sim *sim);
 /* field energy per component, interior cells: out6 = {E1,E2,E3,B1,B2,B3}
  * (emf/diagnostics/os-emf-diagnostics.f03:43-58); summed over this rank only */
 int osgpu_field_energy(osgpu_sim *sim, double *out6);
 /* device-timed duration (ms, CUDA events on the handle's stream) of the last osgpu_step call,
  * summed over its steps: out8 = {emf_bnd, push_deposit, part_bnd, jay_bnd, solver, whole call
- * (first launch to last completion, gaps included), push kernel alone (single species), 0};
+ * (first launch to last completion, gaps included), push kernel alone (single species),
+ * current smooth (also counted inside jay_bnd)};
  * feeds the m_logprof events
  * 'update emf boundary', 'advance deposit', 'update particle boundary', 'update current
  * boundary', 'field solver' (os-logprof.f90:146-260). */

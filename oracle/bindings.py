@@ -73,6 +73,10 @@ class Oracle:
         L.oracle_field_energy.restype = None
         L.oracle_deposit_rho.argtypes = [C.c_int, C.c_int, _i32p, rp, rp, C.c_long, _f64p, _i32p, _i32p]
         L.oracle_deposit_rho.restype = None
+        L.oracle_smooth_setup.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, _i32p, rp]
+        L.oracle_smooth_setup.restype = None
+        L.oracle_smooth.argtypes = [C.c_int, rp, _i32p, _i32p, _i32p, _i32p, C.c_int, rp]
+        L.oracle_smooth.restype = None
         L.oracle_spline.argtypes = [C.c_int, self.creal, rp]
         L.oracle_splineh.argtypes = [C.c_int, self.creal, rp]
         L.oracle_ntrim.argtypes = [self.creal]
@@ -142,6 +146,28 @@ class Oracle:
         size = self._i(grid_shape[::-1][:dim])
         self.lib.oracle_deposit_rho(dim, order, ix, x, q, q.shape[0], rho, size, self._i(gc[0]))
         return rho
+
+
+    SMOOTH_TYPES = {"none": 0, "custom": 1, "binomial": 2, "compensated": 3, "5pass": 4, "tri6": 5,
+                    "tri8": 6, "digital": 11}
+
+    def smooth_setup(self, dim, types, orders, swfj=None, digital_fc=None, digital_A=None):
+        """setup_smooth: returns (order[dim], max_order, scoef[dim, 2*max_order+1])."""
+        ty = self._i([self.SMOOTH_TYPES[t] for t in types])
+        sw = np.zeros((3, 15, 3), np.float64) if swfj is None else np.ascontiguousarray(swfj, np.float64)
+        fc = np.ascontiguousarray(digital_fc if digital_fc is not None else [0.5] * 3, np.float64)
+        A = np.ascontiguousarray(digital_A if digital_A is not None else [60.0] * 3, np.float64)
+        order = np.zeros(3, np.int32)
+        mo = np.zeros(1, np.int32)
+        sc = np.zeros((3, 31), self.dtype)
+        self.lib.oracle_smooth_setup(dim, ty, self._i(orders), sw, fc, A, order, mo, sc.reshape(-1))
+        m = int(mo[0])
+        W = 2 * m + 1
+        return order[:dim].copy(), m, sc.reshape(-1)[:dim * W].reshape(dim, W).copy()
+
+    def smooth(self, dim, f, nx, gc, order, max_order, scoef):
+        self.lib.oracle_smooth(dim, f, self._i(nx), self._i(gc[0]), self._i(gc[1]), self._i(order),
+                               int(max_order), np.ascontiguousarray(scoef, self.dtype))
 
 
 class RefSimd:

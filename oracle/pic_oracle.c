@@ -847,3 +847,170 @@ void oracle_deposit_rho(int dim, int order, const int *ix, const REAL *x, const 
         }
   }
 }
+
+/* ------------------------------------------------------------------------------------
+ * Current smoothing (digital filter), next row 1 of SURVEY.md 8f.
+ *
+ * Kernel set-up: setup_smooth (vdf/os-vdf-smooth.f90:373-467), combine_kernel3 (:155-179),
+ * digital_filter (:117-148), type/order rules of read_nml_smooth (:247-353).  All in double;
+ * the result is stored in REAL (scoef is real(p_k_fld), :49) and THEN normalised in REAL
+ * storage with a double running total (:451-463).
+ * type: 0 none, 1 custom (swfj given), 2 binomial, 3 compensated, 4 5pass, 5 tri6, 6 tri8,
+ * 11 digital.  scoef is [dim][2*max_order+1], centre at index max_order.
+ * ---------------------------------------------------------------------------------- */
+#define SM_ORDER_MAX 15
+static void combine_kernel3(const double (*kern3)[3], int n, int nmax, double *out) {
+  /* out has 2*nmax+1 entries, Fortran index i <-> out[i-1] */
+  for (int i = 0; i < 2 * nmax + 1; i++) out[i] = 0.0;
+  out[nmax] = 1.0;
+  for (int k = 1; k <= n; k++) {
+    double f1 = 0.0, f2;
+    for (int i = (nmax + 1) - (k - 1); i <= (nmax + 1) + k; i++) {
+      const double ci = out[i - 1];
+      out[i - 2] = kern3[k - 1][2] * ci + out[i - 2];
+      f2 = kern3[k - 1][0] * ci;
+      out[i - 1] = kern3[k - 1][1] * ci + f1;
+      f1 = f2;
+    }
+  }
+}
+static double besseli0(double x) { /* besseli0_rdoub, os-math.f90:450-475: polynomial fit; the
+                                       literals without a d exponent are default (single) reals */
+  const double ax = fabs(x);
+  if (ax < 3.75) {
+    const double y = (x / 3.75) * (x / 3.75);
+    return 1.0 + y * ((double)3.5156229f + y * ((double)3.0899424f + y * ((double)1.2067492f +
+           y * ((double)0.2659732f + y * (0.360768e-1 + y * 0.45813e-2)))));
+  }
+  const double y = 3.75 / ax;
+  return (exp(ax) / sqrt(ax)) * ((double)0.39894228f + y * (0.1328592e-1 + y * (0.225319e-2 +
+         y * (-0.157565e-2 + y * (0.916281e-2 + y * (-0.2057706e-1 + y * (0.2635537e-1 +
+         y * (-0.1647633e-1 + y * 0.392377e-2))))))));
+}
+int oracle_smooth_order(int type, int order) { /* read_nml_smooth :280-338 */
+  switch (type) {
+  case 0: return 0;
+  case 3: return order < 2 ? 2 : order;
+  case 4: return 5;
+  case 5: return 3;
+  case 6: return 4;
+  default: return order;
+  }
+}
+void oracle_smooth_setup(int dim, const int *type, const int *order_in, const double *swfj,
+                         const double *digital_fc, const double *digital_A, int *order_out,
+                         int *max_order_out, REAL *scoef) {
+  int max_order = 0;
+  for (int d = 0; d < dim; d++) {
+    order_out[d] = oracle_smooth_order(type[d], order_in[d]);
+    if (order_out[d] > max_order) max_order = order_out[d];
+  }
+  *max_order_out = max_order;
+  const int W = 2 * max_order + 1;
+  for (int i = 0; i < dim * W; i++) scoef[i] = R(0.0);
+  for (int d = 0; d < dim; d++) {
+    const int n = order_out[d];
+    if (n == 0) continue;
+    double kern3[SM_ORDER_MAX][3], comb[2 * SM_ORDER_MAX + 3];
+    REAL *s = scoef + d * W;
+    int have = 1;
+    switch (type[d]) {
+    case 1: /* custom: swfj(3, p_order_max, p_x_dim) */
+      for (int j = 0; j < n; j++)
+        for (int c = 0; c < 3; c++) kern3[j][c] = swfj[(d * SM_ORDER_MAX + j) * 3 + c];
+      break;
+    case 2:
+      for (int j = 0; j < n; j++) { kern3[j][0] = 1.0; kern3[j][1] = 2.0; kern3[j][2] = 1.0; }
+      break;
+    case 3: {
+      for (int j = 0; j < n - 1; j++) { kern3[j][0] = 1.0; kern3[j][1] = 2.0; kern3[j][2] = 1.0; }
+      /* comp = ( 4.0 + 2.0 * ( order - 1 ) ) / ( order - 1 ): default-real arithmetic (:418) */
+      const double comp = (double)((4.0f + 2.0f * (float)(n - 1)) / (float)(n - 1));
+      kern3[n - 1][0] = -1.0; kern3[n - 1][1] = comp; kern3[n - 1][2] = -1.0;
+      break;
+    }
+    case 4:
+      for (int j = 0; j < 4; j++) { kern3[j][0] = 1.0; kern3[j][1] = 2.0; kern3[j][2] = 1.0; }
+      kern3[4][0] = -5.0; kern3[4][1] = 15.0; kern3[4][2] = -5.0;
+      break;
+    case 5: {
+      static const double t6[7] = {0.015625, -0.09375, 0.234375, 0.6875, 0.234375, -0.09375, 0.015625};
+      for (int i = 0; i < 7; i++) s[max_order - 3 + i] = R(t6[i]);
+      have = 0;
+      break;
+    }
+    case 6: {
+      static const double t8[9] = {-0.00390625, 0.03125, -0.109375, 0.21875, 0.7265625,
+                                   0.21875, -0.109375, 0.03125, -0.00390625};
+      for (int i = 0; i < 9; i++) s[max_order - 4 + i] = R(t8[i]);
+      have = 0;
+      break;
+    }
+    case 11: {
+      const double A = digital_A[d], fc = digital_fc[d], pi = 3.14159265358979323846264;
+      double alpha;
+      if (A <= 21.) alpha = 0.;
+      else if (A >= 50.) alpha = 0.1102 * (A - 8.7);
+      else alpha = 0.5842 * pow(A - 21., 0.4) + 0.07886 * (A - 21.);
+      s[max_order] = R(fc);
+      for (int i = 1; i <= n; i++) {
+        const float r = (float)i / (float)n; /* real(i)/n is default real (:139) */
+        const double v = besseli0(alpha * sqrt(1.0 - (double)(r * r))) / besseli0(alpha) *
+                         sin(i * pi * fc) / (i * pi);
+        s[max_order + i] = R(v);
+        s[max_order - i] = R(v);
+      }
+      have = 0;
+      break;
+    }
+    default: have = 0; break;
+    }
+    if (have) {
+      combine_kernel3((const double(*)[3])kern3, n, max_order, comb);
+      for (int i = 0; i < W; i++) s[i] = R(comb[i]);
+    }
+    /* normalise (:451-463) */
+    double total = 0.0;
+    for (int j = max_order - n; j <= max_order + n; j++) total = total + (double)s[j];
+    for (int j = max_order - n; j <= max_order + n; j++) s[j] = R((double)s[j] / total);
+  }
+}
+
+/* filter_2d / filter_3d (vdf/os-vdf-smooth.f90:639-828, 834-1105): separable, in place, axis by
+ * axis, over the WHOLE extent of the other axes (guard cells included) and ext_lb+order ..
+ * ext_ub-order along the axis; the sliding window o() holds the unfiltered values.  Sum order:
+ * f = o(-n)*s(-n); f = f + o(k)*s(k), k = -n+1..n, separate multiply and add in REAL.
+ * (The reference's z pass loads the new window value into o(:,nsm2) instead of o(:,nsm3),
+ * :1032-1034 -- identical when order(2) == order(3), as in every shipped deck; this restatement
+ * uses nsm3.)  f: (3, S1, S2[, S3]) with S = nx + gcl + gcu. */
+void oracle_smooth(int dim, REAL *f, const int *nx, const int *gcl, const int *gcu,
+                   const int *order, int max_order, const REAL *scoef) {
+  long S[3] = {1, 1, 1}, st[3];
+  for (int d = 0; d < dim; d++) S[d] = nx[d] + gcl[d] + gcu[d];
+  st[0] = 3; st[1] = 3 * S[0]; st[2] = 3 * S[0] * S[1];
+  const int W = 2 * max_order + 1;
+  for (int ax = 0; ax < dim; ax++) {
+    const int n = order[ax];
+    if (n <= 0) continue;
+    const REAL *s = scoef + ax * W + max_order; /* s[k], k = -n..n */
+    const int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+    REAL o[3][2 * SM_ORDER_MAX + 1];
+    for (long j2 = 0; j2 < S[a2]; j2++)
+      for (long j1 = 0; j1 < S[a1]; j1++) {
+        REAL *line = f + j1 * st[a1] + j2 * st[a2];
+        const long lb = n, ub = S[ax] - 1 - n; /* int_lb, int_ub in padded coordinates */
+        for (int k = -n; k < n; k++)
+          for (int c = 0; c < 3; c++) o[c][k + n] = line[(lb + k) * st[ax] + c];
+        for (long i = lb; i <= ub; i++) {
+          for (int c = 0; c < 3; c++) o[c][2 * n] = line[(i + n) * st[ax] + c];
+          REAL v[3];
+          for (int c = 0; c < 3; c++) v[c] = o[c][0] * s[-n];
+          for (int k = -n + 1; k <= n; k++)
+            for (int c = 0; c < 3; c++) v[c] = v[c] + o[c][k + n] * s[k];
+          for (int k = 0; k < 2 * n; k++)
+            for (int c = 0; c < 3; c++) o[c][k] = o[c][k + 1];
+          for (int c = 0; c < 3; c++) line[i * st[ax] + c] = v[c];
+        }
+      }
+  }
+}

@@ -30,10 +30,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, defines=()):
+    """variant/defines: build libosiris_b200_<variant>.so with extra -D flags (A/B runs of kernel
+    variants, selected at run time with OSGPU_LIB); the default build takes neither."""
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "osiris_b200.h"))
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not variant else f"build_{variant}")
+    out = OUT if not variant else os.path.join(HERE, f"libosiris_b200_{variant}.so")
+    flags = FLAGS + [f"-D{d}" for d in defines]
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     objs = []
@@ -42,7 +46,7 @@ def build(force=False, verbose=False):
         o = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([NVCC] + FLAGS + ["-c", s, "-o", o])
+            jobs.append([NVCC] + flags + ["-c", s, "-o", o])
 
     def run(cmd):
         if verbose:
@@ -54,11 +58,14 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         list(ex.map(run, jobs))
-    if jobs or force or _stale(OUT, objs):
-        run([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+    if jobs or force or _stale(out, objs):
+        run([NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                    "-Xcompiler", "-fPIC", "-ldl", "-lpthread", "-lrt"])
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    # python -m osiris_b200.build [--force] [--variant NAME -DX=1 -DY=2 ...]
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose=True, variant=var,
+                defines=[a[2:] for a in sys.argv if a.startswith("-D")]))

@@ -7,6 +7,8 @@
 //
 // All arithmetic is written as separate multiplies and adds in the reference's order (the unit is
 // compiled with -fmad=false), so E and B are bit-identical to the Fortran statement.
+#include <utility>
+
 #include "common.cuh"
 #include "fields.cuh"
 
@@ -94,6 +96,64 @@ template int yee_advance<float>(const Grid &, Field3<float>, Field3<float>, Fiel
                                 const double *, double, cudaStream_t, long long *);
 template int yee_advance<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>,
                                  const double *, double, cudaStream_t, long long *);
+
+// ---------------------------------------------------------------------------------------------
+// Current smoothing: one pass of the separable digital filter along `axis`, src -> dst
+// (filter_2d / filter_3d, source/vdf/os-vdf-smooth.f90:639-828, 834-1105).  The reference filters
+// in place with a sliding window of unfiltered values; out of place that is dst = filter(src).
+// Filtered range: box[axis] shrunk by n on both sides, whole box extent on the other axes (guard
+// cells included); every other point is copied.  Sum order as the reference: f = o(-n)*s(-n),
+// then f = f + o(k)*s(k) for k = -n+1..n, separate multiply and add (-fmad=false).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+    smooth_axis_kernel(Field3<T> dst, Field3<const T> src, Grid g, SmoothBox bx, int axis, int n, SmoothCoef<T> sc) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= g.S[0]) return;
+  const int i1 = blockIdx.y, i2 = blockIdx.z;
+  const long long p = g.at(i0, i1, i2);
+  const int i[3] = {i0, i1, i2};
+  bool in = true;
+#pragma unroll
+  for (int d = 0; d < 3; d++) in &= (i[d] >= bx.lo[d]) && (i[d] <= bx.hi[d]);
+  in &= (i[axis] >= bx.lo[axis] + n) && (i[axis] <= bx.hi[axis] - n);
+  const long long stride = (axis == 0) ? 1 : (axis == 1 ? (long long)g.P0 : (long long)g.P0 * g.S[1]);
+  const T *s = sc.s + SMOOTH_ORDER_MAX;  // s[k], k = -n..n
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const T *q = src.c[c] + p;
+    T v;
+    if (in) {
+      v = q[-n * stride] * s[-n];
+      for (int k = -n + 1; k <= n; k++) v = v + q[k * stride] * s[k];
+    } else {
+      v = q[0];
+    }
+    dst.c[c][p] = v;
+  }
+}
+
+template <typename T>
+int smooth_current(const Grid &g, Field3<T> jay, Field3<T> tmp, const SmoothBox &bx, const int *order,
+                   const SmoothCoef<T> *coef, cudaStream_t st, long long *launches) {
+  Field3<T> a = jay, b = tmp;
+  const dim3 blk(128), grid((g.S[0] + 127) / 128, g.S[1], g.S[2]);
+  for (int ax = 0; ax < g.dim; ax++) {
+    if (order[ax] <= 0) continue;
+    Field3<const T> ca{{a.c[0], a.c[1], a.c[2]}};
+    smooth_axis_kernel<T><<<grid, blk, 0, st>>>(b, ca, g, bx, ax, order[ax], coef[ax]);
+    *launches += 1;
+    std::swap(a, b);
+  }
+  OSGPU_CUDA(cudaGetLastError());
+  if (a.c[0] != jay.c[0])  // odd number of passes: the result sits in the scratch planes (contiguous)
+    OSGPU_CUDA(cudaMemcpyAsync(jay.c[0], a.c[0], sizeof(T) * 3 * g.vol, cudaMemcpyDeviceToDevice, st));
+  return OSGPU_OK;
+}
+template int smooth_current<float>(const Grid &, Field3<float>, Field3<float>, const SmoothBox &, const int *,
+                                   const SmoothCoef<float> *, cudaStream_t, long long *);
+template int smooth_current<double>(const Grid &, Field3<double>, Field3<double>, const SmoothBox &, const int *,
+                                    const SmoothCoef<double> *, cudaStream_t, long long *);
 
 // ---------------------------------------------------------------------------------------------
 // Slab helpers.  A slab is the padded range [a0, a1] along `axis` times the full padded extent of

@@ -19,6 +19,19 @@ long long slab_volume(const Grid &g, int axis, int a0, int a1);
 template <typename T>
 int layout_convert(const Grid &g, Field3<T> f, T *aos, const int *hsize, const int *hgc, int to_device,
                    cudaStream_t st, long long *launches);
+// current smoothing (vdf/os-vdf-smooth.f90): filter kernel of one axis, centre at SMOOTH_ORDER_MAX
+// (p_order_max = 15, os-vdf-smooth.f90:34), and the box of the t_vdf's own extent in padded coordinates
+constexpr int SMOOTH_ORDER_MAX = 15;
+template <typename T> struct SmoothCoef {
+  T s[2 * SMOOTH_ORDER_MAX + 1];
+};
+struct SmoothBox {
+  int lo[3], hi[3];
+};
+// jay and tmp: three contiguous component planes each (c[1] = c[0] + vol, c[2] = c[0] + 2 vol)
+template <typename T>
+int smooth_current(const Grid &g, Field3<T> jay, Field3<T> tmp, const SmoothBox &bx, const int *order,
+                   const SmoothCoef<T> *coef, cudaStream_t st, long long *launches);
 template <typename T>
 int field_energy(const Grid &g, T *const *comps6, double *dev_out6, cudaStream_t st, long long *launches);
 

@@ -764,7 +764,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     // The warps take runs of PB * 32 particles from a counter (a warp that finished its deposit
     // early sorts more); PB particles per thread in flight: the scratch range sits in L2, latency
     // is what costs.
-    constexpr int PB = 2;
+#ifndef SORT_PB
+#define SORT_PB 2
+#endif
+    constexpr int PB = SORT_PB;
     const T *scr0 = a.scc.base + (so >> 5) * P::CHUNK_WORDS + lane;
     T *dstb = a.spc.base + (off >> 5) * P::CHUNK_WORDS;
     for (;;) {

@@ -52,6 +52,8 @@ struct SimBase {
   virtual int sort() = 0;
   virtual int current_update_boundary() = 0;
   virtual int emf_advance() = 0;
+  virtual int current_set_smooth(const int *order, int max_order, const void *scoef) = 0;
+  virtual int current_smooth() = 0;
   virtual int field_energy6(double *out6) = 0;
   virtual int phase_times(double *out6) = 0;
   virtual int finalize() = 0;
@@ -104,6 +106,29 @@ template <typename T> struct Sim final : SimBase {
   double slack = 0.25;
   int push_events = 0;
   int n_sm = 1, push_bps = 1;  // SMs, resident push CTAs per SM
+  // current smoothing (t_current%curr_smooth): per-axis order and filter kernel, scratch planes
+  bool smooth_on = false;
+  int sm_order[3] = {0, 0, 0};
+  SmoothCoef<T> sm_coef[3];
+  T *jtmp = nullptr;
+  cudaEvent_t ev_sm[2];
+  // device staging area of the host-array transfers (fill_data in both directions): kept between
+  // calls and only ever grown, so a host that moves a species every step does not pay a multi-GB
+  // cudaMalloc/cudaFree per transfer
+  char *stage_mem = nullptr;
+  size_t stage_cap = 0;
+  int stage_get(size_t bytes, char **out) {
+    if (bytes > stage_cap) {
+      if (stage_mem) cudaFree(stage_mem);
+    if (jtmp) cudaFree(jtmp);
+      stage_mem = nullptr;
+      stage_cap = 0;
+      OSGPU_CUDA(cudaMalloc(&stage_mem, bytes));
+      stage_cap = bytes;
+    }
+    *out = stage_mem;
+    return OSGPU_OK;
+  }
 
   // ---------------------------------------------------------------------------------------
   int init(const osgpu_config *c, const void *nccl_id) {
@@ -131,6 +156,7 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaSetDevice(dev));
     OSGPU_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &e : ev) OSGPU_CUDA(cudaEventCreate(&e));
+    for (auto &e : ev_sm) OSGPU_CUDA(cudaEventCreate(&e));
 
     g.dim = dim;
     for (int d = 0; d < 3; d++) {
@@ -358,7 +384,7 @@ template <typename T> struct Sim final : SimBase {
     char *stage = nullptr;
     const size_t al = 256;
     auto up = [&](size_t v) { return (v + al - 1) / al * al; };
-    OSGPU_CUDA(cudaMalloc(&stage, up(bix) + up(bx) + up(bp) + up(bq) + up(btag) + al));
+    OSGPU_TRY(stage_get(up(bix) + up(bx) + up(bp) + up(bq) + up(btag) + al, &stage));
     AosParticles<T> in;
     char *c = stage;
     in.ix = (const int *)c; c += up(bix);
@@ -402,7 +428,6 @@ template <typename T> struct Sim final : SimBase {
         rc = OSGPU_ERR_CUDA;
       }
     } while (0);
-    cudaFree(stage);
     return rc;
   }
 
@@ -438,7 +463,7 @@ template <typename T> struct Sim final : SimBase {
     const size_t al = 256;
     auto up = [&](size_t v) { return (v + al - 1) / al * al; };
     char *stage = nullptr;
-    OSGPU_CUDA(cudaMalloc(&stage, up(bix) + up(bx) + up(bp) + up(bq) + up(btag) + up(boff) + al));
+    OSGPU_TRY(stage_get(up(bix) + up(bx) + up(bp) + up(bq) + up(btag) + up(boff) + al, &stage));
     char *c = stage;
     int *oix = (int *)c; c += up(bix);
     T *ox = (T *)c; c += up(bx);
@@ -461,7 +486,6 @@ template <typename T> struct Sim final : SimBase {
         rc = OSGPU_ERR_CUDA;
       }
     } while (0);
-    cudaFree(stage);
     return rc;
   }
 
@@ -470,8 +494,9 @@ template <typename T> struct Sim final : SimBase {
     int hs[3] = {1, 1, 1}, hg[3] = {0, 0, 0};
     for (int d = 0; d < dim; d++) { hs[d] = g.nx[d] + gc[0][d] + gc[1][d]; hg[d] = gc[0][d]; }
     const size_t bytes = sizeof(T) * 3 * (size_t)hs[0] * hs[1] * hs[2];
-    T *stage = nullptr;
-    OSGPU_CUDA(cudaMalloc(&stage, bytes));
+    char *stage_c = nullptr;
+    OSGPU_TRY(stage_get(bytes, &stage_c));
+    T *stage = reinterpret_cast<T *>(stage_c);
     int rc = OSGPU_OK;
     if (to_device) {
       if (cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = OSGPU_ERR_CUDA;
@@ -482,7 +507,6 @@ template <typename T> struct Sim final : SimBase {
     }
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == OSGPU_OK) rc = OSGPU_ERR_CUDA;
     if (rc == OSGPU_ERR_CUDA) set_error("field transfer failed: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaFree(stage);
     return rc;
   }
   int fields_upload(const void *e, const void *b) override {
@@ -533,6 +557,48 @@ template <typename T> struct Sim final : SimBase {
     return update_guards(comps, 3, 1);
   }
   int emf_advance() override { return yee_advance<T>(g, E, B, J, cfg.dx, cfg.dt, st, &launches); }
+
+  // setup_smooth's result (vdf/os-vdf-smooth.f90:373-467): order(1:D) and scoef(2*max_order+1, D)
+  // in field precision, centre at max_order + 1.  The filtered current must cover 1..nx+1 (Yee):
+  // gc_jay >= (order, order + 1), the reference's own rule (current/os-current-define.f03:199-205).
+  int current_set_smooth(const int *order, int max_order, const void *scoef) override {
+    if (max_order < 0 || max_order > SMOOTH_ORDER_MAX) { set_error("smooth: max_order %d outside 0..%d", max_order, SMOOTH_ORDER_MAX); return OSGPU_ERR_INVALID; }
+    bool any = false;
+    for (int d = 0; d < dim; d++) {
+      if (order[d] < 0 || order[d] > max_order) { set_error("smooth: order(%d) = %d outside 0..max_order", d + 1, order[d]); return OSGPU_ERR_INVALID; }
+      if (order[d] > 0 && (cfg.gc_jay[0][d] < order[d] || cfg.gc_jay[1][d] < order[d] + 1)) {
+        set_error("smooth: axis %d needs current guard cells (%d,%d), has (%d,%d)", d + 1, order[d], order[d] + 1,
+                  cfg.gc_jay[0][d], cfg.gc_jay[1][d]);
+        return OSGPU_ERR_INVALID;
+      }
+      any |= order[d] > 0;
+    }
+    const T *sc = static_cast<const T *>(scoef);
+    const int W = 2 * max_order + 1;
+    for (int d = 0; d < 3; d++) {
+      sm_order[d] = (d < dim) ? order[d] : 0;
+      for (int k = 0; k < 2 * SMOOTH_ORDER_MAX + 1; k++) sm_coef[d].s[k] = T(0);
+      if (d < dim && sc)
+        for (int k = -max_order; k <= max_order; k++) sm_coef[d].s[SMOOTH_ORDER_MAX + k] = sc[d * W + max_order + k];
+    }
+    if (any && !sc) { set_error("smooth: scoef is null"); return OSGPU_ERR_INVALID; }
+    if (any && !jtmp) OSGPU_CUDA(cudaMalloc(&jtmp, sizeof(T) * 3 * g.vol));
+    smooth_on = any;
+    return OSGPU_OK;
+  }
+  int current_smooth() override {  // jay%smooth(), after update_boundary (os-simulation.f03:654-657)
+    if (!smooth_on) return OSGPU_OK;
+    SmoothBox bx;
+    for (int d = 0; d < 3; d++) {  // the t_vdf's own bounds 1-gc_lower .. nx+gc_upper, padded coordinates
+      bx.lo[d] = (d < dim) ? g.gl[d] - cfg.gc_jay[0][d] : 0;
+      bx.hi[d] = (d < dim) ? g.gl[d] + g.nx[d] + cfg.gc_jay[1][d] - 1 : 0;
+    }
+    Field3<T> tmp{{jtmp, jtmp + g.vol, jtmp + 2 * g.vol}};
+    OSGPU_CUDA(cudaEventRecord(ev_sm[0], st));
+    OSGPU_TRY(smooth_current<T>(g, J, tmp, bx, sm_order, sm_coef, st, &launches));
+    OSGPU_CUDA(cudaEventRecord(ev_sm[1], st));
+    return OSGPU_OK;
+  }
 
   // ---------------------------------------------------------------------------------------
   int advance_deposit(double *ene) override {
@@ -684,6 +750,7 @@ template <typename T> struct Sim final : SimBase {
       }
       OSGPU_CUDA(cudaEventRecord(ev[3], st));
       OSGPU_TRY(current_update_boundary());
+      OSGPU_TRY(current_smooth());
       OSGPU_CUDA(cudaEventRecord(ev[4], st));
       OSGPU_TRY(emf_advance());
       OSGPU_CUDA(cudaEventRecord(ev[5], st));
@@ -695,6 +762,11 @@ template <typename T> struct Sim final : SimBase {
         float ms = 0;
         OSGPU_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
         phase_ms[k] += ms;
+      }
+      if (smooth_on) {  // 'current smooth' (also inside the current-boundary interval)
+        float ms = 0;
+        OSGPU_CUDA(cudaEventElapsedTime(&ms, ev_sm[0], ev_sm[1]));
+        phase_ms[7] += ms;
       }
     }
     OSGPU_CUDA(cudaEventRecord(ev[7], st));
@@ -731,6 +803,7 @@ template <typename T> struct Sim final : SimBase {
     for (auto &b : xbuf) cudaFree(b);
     for (auto &b : pbuf) cudaFree(b);
     cudaFree(fld); cudaFree(d_err); cudaFree(d_cnt); cudaFree(d_fe);
+    if (stage_mem) cudaFree(stage_mem);
     if (h_pin) cudaFreeHost(h_pin);
     nccl.destroy();
     for (auto &e : ev) cudaEventDestroy(e);
@@ -852,6 +925,12 @@ int osgpu_particles_update_boundary(osgpu_sim *h) { H_CHECK(h); return h->impl->
 int osgpu_sort(osgpu_sim *h) { H_CHECK(h); return h->impl->sort(); }
 int osgpu_current_update_boundary(osgpu_sim *h) { H_CHECK(h); return h->impl->current_update_boundary(); }
 int osgpu_emf_advance(osgpu_sim *h) { H_CHECK(h); return h->impl->emf_advance(); }
+int osgpu_current_set_smooth(osgpu_sim *h, const int *order, int max_order, const void *scoef) {
+  H_CHECK(h);
+  if (!order) { osgpu::set_error("smooth: order is null"); return OSGPU_ERR_INVALID; }
+  return h->impl->current_set_smooth(order, max_order, scoef);
+}
+int osgpu_current_smooth(osgpu_sim *h) { H_CHECK(h); return h->impl->current_smooth(); }
 int osgpu_field_energy(osgpu_sim *h, double *out6) { H_CHECK(h); return h->impl->field_energy6(out6); }
 int osgpu_phase_times_ms(osgpu_sim *h, double *out6) { H_CHECK(h); return h->impl->phase_times(out6); }
 int64_t osgpu_launch_count(osgpu_sim *h) { return h ? h->impl->launches : 0; }

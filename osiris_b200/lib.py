@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libosiris_b200.so")
+LIBPATH = os.environ.get("OSGPU_LIB") or os.path.join(HERE, "libosiris_b200.so")  # (OSGPU_LIB: kernel-variant A/B runs)
 
 OSGPU_OK = 0
 ERR_NAMES = {-1: "INVALID", -2: "CUDA", -3: "NCCL", -4: "CAPACITY", -5: "STABILITY", -6: "NO_DEVICE"}
@@ -68,8 +68,9 @@ def load():
     L.osgpu_current_download.argtypes = [vp, vp]
     L.osgpu_step.argtypes = [vp, C.c_int, dp]
     for name in ("osgpu_emf_update_boundary", "osgpu_particles_update_boundary", "osgpu_sort",
-                 "osgpu_current_update_boundary", "osgpu_emf_advance", "osgpu_sync"):
+                 "osgpu_current_update_boundary", "osgpu_emf_advance", "osgpu_sync", "osgpu_current_smooth"):
         getattr(L, name).argtypes = [vp]
+    L.osgpu_current_set_smooth.argtypes = [vp, vp, C.c_int, vp]
     L.osgpu_advance_deposit.argtypes = [vp, dp]
     L.osgpu_field_energy.argtypes = [vp, dp]
     L.osgpu_phase_times_ms.argtypes = [vp, dp]
@@ -127,5 +128,6 @@ EXPORTS = [
     "osgpu_current_download", "osgpu_step", "osgpu_emf_update_boundary", "osgpu_advance_deposit",
     "osgpu_particles_update_boundary", "osgpu_sort", "osgpu_current_update_boundary", "osgpu_emf_advance",
     "osgpu_field_energy", "osgpu_phase_times_ms", "osgpu_launch_count", "osgpu_stream", "osgpu_sync",
-    "osgpu_host_alloc", "osgpu_host_free", "osgpu_vadvance_deposit",
+    "osgpu_host_alloc", "osgpu_host_free", "osgpu_vadvance_deposit", "osgpu_current_set_smooth",
+    "osgpu_current_smooth",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -134,6 +134,22 @@ class _Current:
     def update_boundary(self):
         check(self.sim._L.osgpu_current_update_boundary(self.sim._h))
 
+    def set_smooth(self, smooth):
+        """Hand setup_smooth's result (osiris_b200.smooth.Smooth) to the device; None switches it off."""
+        if smooth is None or not smooth.if_smooth():
+            order = np.zeros(3, np.int32)
+            check(self.sim._L.osgpu_current_set_smooth(self.sim._h, ptr(order), 0, None))
+            return
+        sc = smooth.scoef if smooth.scoef is not None else smooth.setup(self.sim.dx, dtype=self.sim.dtype)
+        sc = np.ascontiguousarray(sc, self.sim.dtype)
+        order = np.zeros(3, np.int32)
+        order[:self.sim.dim] = smooth.order
+        check(self.sim._L.osgpu_current_set_smooth(self.sim._h, ptr(order), int(smooth.max_order), ptr(sc)))
+
+    def smooth(self):
+        """jay%smooth() (current/os-current-define.f03:298-316)"""
+        check(self.sim._L.osgpu_current_smooth(self.sim._h))
+
 
 class _Particles:
     """t_particles (particles/os-particles.f03): the container of all species"""
@@ -159,7 +175,7 @@ class Simulation:
     """The hot part of t_simulation (os-simulation.f03).  One instance per rank / GPU."""
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
-                 node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True):
+                 node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
@@ -169,6 +185,8 @@ class Simulation:
         lo, up = min_gc(self.order, smooth_order)
         self.gc_emf = gc_emf if gc_emf is not None else ([lo] * dim, [up] * dim)
         self.gc_jay = gc_jay if gc_jay is not None else ([lo] * dim, [up] * dim)
+        if smooth is not None and gc_jay is None:  # setup of t_current (current/os-current-define.f03:192-205)
+            self.gc_jay = smooth.gc_num(self.gc_jay)
         self.no_co = node_conf if node_conf is not None else NodeConf(dim)
         cfg = Config()
         cfg.dim, cfg.order, cfg.real_bytes, cfg.nspecies = self.dim, self.order, np.dtype(self.dtype).itemsize, nspecies
@@ -193,6 +211,8 @@ class Simulation:
         check(self._L.osgpu_init(C.byref(self._h), C.byref(cfg), idbuf))
         self.emf, self.jay, self.part = _Emf(self), _Current(self), _Particles(self)
         self.nspecies = nspecies
+        if smooth is not None:
+            self.jay.set_smooth(smooth)
 
     # padded host array shapes (numpy order: slowest first, component last)
     def _shape(self, gc):
@@ -222,7 +242,8 @@ class Simulation:
         out = np.zeros(8, np.float64)
         check(self._L.osgpu_phase_times_ms(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return dict(zip(("update emf boundary", "advance deposit", "update particle boundary",
-                         "update current boundary", "field solver", "loop", "push kernel"), [float(v) for v in out]))
+                         "update current boundary", "field solver", "loop", "push kernel", "current smooth"),
+                        [float(v) for v in out]))
 
     @property
     def launch_count(self):

@@ -7,7 +7,7 @@ from oracle.bindings import Oracle, aligned
 
 
 class OracleSim:
-    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None):
+    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None):
         self.orc = Oracle(precision)
         self.dtype = self.orc.dtype
         self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
@@ -19,6 +19,7 @@ class OracleSim:
         self.b = np.zeros(sh(self.gc_emf), self.dtype)
         self.j = np.zeros(sh(self.gc_jay), self.dtype)
         self.species = []
+        self.smooth = smooth  # (order[dim], max_order, scoef[dim, 2 max_order + 1]) from Oracle.smooth_setup
         # particles use dt rounded to their precision (spec/os-spec-vpush.f03:374)
         self.dtp = float(self.dtype(self.dt))
 
@@ -52,6 +53,11 @@ class OracleSim:
     def current_update_boundary(self):
         self.orc.update_periodic(self.dim, self.j, self.nx, self.gc_jay, "add")
 
+    def current_smooth(self):
+        if self.smooth is not None:
+            order, mo, sc = self.smooth
+            self.orc.smooth(self.dim, self.j, self.nx, self.gc_jay, order, mo, sc)
+
     def emf_advance(self):
         assert self.gc_emf == self.gc_jay
         self.orc.yee_advance(self.dim, self.e, self.b, self.j, self.nx, self.gc_emf, self.dx, self.dt)
@@ -63,6 +69,7 @@ class OracleSim:
             ene = self.advance_deposit()
             self.particles_update_boundary()
             self.current_update_boundary()
+            self.current_smooth()
             self.emf_advance()
         return ene
 

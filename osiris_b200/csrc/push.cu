@@ -172,10 +172,9 @@ template <int DIM> __device__ __forceinline__ int linear_cell(const int *l) {
   else return l[0] + G::TX * (l[1] + G::TY * l[DIM - 1]);
 }
 
-// N independent shared-memory adds with two round trips instead of N serialised compare-and-swap
-// loops (fp32/fp64 atomicAdd on shared memory is an ATOMS.CAST.SPIN loop on sm_100a): read all the
-// old values, then try every update with one CAS each; an update that lost a race falls back to
-// the ordinary atomicAdd.  The addresses of one batch must not alias inside the warp.
+// Optimistic shared-memory add: fp32/fp64 atomicAdd on shared memory is an ATOMS.CAST.SPIN loop
+// on sm_100a, so independent updates are issued as "read the old values, then one compare-and-swap
+// each"; an update that lost a race falls back to the ordinary atomicAdd.
 __device__ __forceinline__ bool cas_add(float *p, float old, float v) {
   const int o = __float_as_int(old);
   return atomicCAS(reinterpret_cast<int *>(p), o, __float_as_int(old + v)) == o;
@@ -185,48 +184,38 @@ __device__ __forceinline__ bool cas_add(double *p, double old, double v) {
   return atomicCAS(reinterpret_cast<unsigned long long *>(p), o,
                    (unsigned long long)__double_as_longlong(old + v)) == o;
 }
-template <typename T, int N> __device__ __forceinline__ void add_batch(T *const (&p)[N], const T (&v)[N]) {
-  T old[N];
-#pragma unroll
-  for (int k = 0; k < N; k++) old[k] = *reinterpret_cast<volatile T *>(p[k]);
-#pragma unroll
-  for (int k = 0; k < N; k++)
-    if (!cas_add(p[k], old[k], v[k])) atomicAdd(p[k], v[k]);
-}
-
-// Flush of a cell's stencil accumulators into the shared J tile: one batch per component and z
-// plane (inside a batch the addresses of a lane are distinct; lanes of a warp hold unrelated cells,
-// an update that collides with another lane's falls back to the atomic).
+// Flush of a cell's stencil accumulators into the shared J tile.  One batch = the same stencil
+// point (k1, k2, k3) of the three components: they live in three different arrays, and the lanes of
+// a warp hold different cells, so no two updates of a batch can alias inside the warp and the
+// optimistic compare-and-swap only ever loses against another warp.  (Batches of a whole x-y plane
+// of one component made lanes that own neighbouring cells invalidate each other's old values:
+// about half of the lanes fell back to the spin loop on every entry -- profiles/r1_notes.md.)
 template <int DIM, int ORDER, typename T, class P>
 __device__ __forceinline__ void flush_stencil(const T *acc, T *pj) {
   using G = Tile<DIM, ORDER, T>;
   constexpr int NP = G::NP;
   constexpr int NZ = (DIM == 3) ? NP : 1;
 #pragma unroll
-  for (int comp = 0; comp < 3; comp++) {
-    constexpr int N1[3] = {NP - 1, NP, NP}, N2[3] = {NP, NP - 1, NP};
+  for (int k3 = 0; k3 < NZ; k3++)
 #pragma unroll
-    for (int k3 = 0; k3 < NZ; k3++) {
-      if (DIM == 3 && comp == 2 && k3 >= NP - 1) continue;
-      const int n1 = N1[comp], n2 = N2[comp];
-      T *bp[NP * NP];
-      T bv[NP * NP];
+    for (int k2 = 0; k2 < NP; k2++)
 #pragma unroll
-      for (int k = 0; k < NP * NP; k++) {  // (entries beyond n1 * n2 repeat the last one with a zero)
-        const int k1 = (k < n1 * n2) ? k % n1 : 0, k2 = (k < n1 * n2) ? k / n1 : 0;
-        bp[k] = pj + comp * G::JVOL + k1 + G::JX * (k2 + G::JY * k3);
-        bv[k] = acc[P::acc_index(comp, k1, k2, k3)];
+      for (int k1 = 0; k1 < NP; k1++) {
+        const bool on[3] = {k1 < NP - 1, k2 < NP - 1, DIM == 2 || k3 < NP - 1};
+        T *p[3];
+        T old[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          p[c] = pj + c * G::JVOL + k1 + G::JX * (k2 + G::JY * k3);
+          if (on[c]) old[c] = *reinterpret_cast<volatile T *>(p[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          if (!on[c]) continue;
+          const T v = acc[P::acc_index(c, k1, k2, k3)];
+          if (!cas_add(p[c], old[c], v)) atomicAdd(p[c], v);
+        }
       }
-      if (comp == 2) add_batch<T, NP * NP>(bp, bv);
-      else {
-        T *cp[NP * (NP - 1)];
-        T cv[NP * (NP - 1)];
-#pragma unroll
-        for (int k = 0; k < NP * (NP - 1); k++) { cp[k] = bp[k]; cv[k] = bv[k]; }
-        add_batch<T, NP * (NP - 1)>(cp, cv);
-      }
-    }
-  }
 }
 
 template <int DIM, int ORDER, typename T>

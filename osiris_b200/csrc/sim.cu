@@ -120,7 +120,6 @@ template <typename T> struct Sim final : SimBase {
   int stage_get(size_t bytes, char **out) {
     if (bytes > stage_cap) {
       if (stage_mem) cudaFree(stage_mem);
-    if (jtmp) cudaFree(jtmp);
       stage_mem = nullptr;
       stage_cap = 0;
       OSGPU_CUDA(cudaMalloc(&stage_mem, bytes));
@@ -804,6 +803,8 @@ template <typename T> struct Sim final : SimBase {
     for (auto &b : pbuf) cudaFree(b);
     cudaFree(fld); cudaFree(d_err); cudaFree(d_cnt); cudaFree(d_fe);
     if (stage_mem) cudaFree(stage_mem);
+    if (jtmp) cudaFree(jtmp);
+    stage_mem = nullptr; stage_cap = 0; jtmp = nullptr;
     if (h_pin) cudaFreeHost(h_pin);
     nccl.destroy();
     for (auto &e : ev) cudaEventDestroy(e);

@@ -33,6 +33,9 @@ namespace osgpu {
 
 using namespace pic;
 
+#ifndef OSGPU_HALO_JOBS
+#define OSGPU_HALO_JOBS 1
+#endif
 constexpr int NTHREADS = 256;
 static_assert(NTHREADS == TILE_NCELL, "one thread per tile cell");
 
@@ -141,12 +144,12 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // momentum slots hold the end point of the trajectory), above them one region per warp with the
   // list of pieces that belong to other cells of the tile and the queue of particles to split, and
   // at the top the CTA's list of pieces that lie in halo cells
-  static constexpr int BUF_BYTES = FAST ? 74752 : 0;
+  static constexpr int BUF_BYTES = FAST ? 74752 - (OSGPU_PAD_EY && DIM == 3 && ORDER == 2 && sizeof(T) == 4 ? 2304 : 0) : 0;  // (2 CTAs per SM: the padded 3D quadratic E/B tile takes 2304 B more)
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
   static constexpr int XMIN = 20;  // list entries per warp always available
-  static constexpr int HCAP = 96;  // CTA-wide list of pieces in halo cells (top of the buffer)
-  static constexpr int TCAP = FAST ? (((BUF_WORDS - NWARP * (XMIN * XW + QWORDS) - HCAP * XW) / NC) & ~255) : (1 << 30);
-  static constexpr int NROUND = FAST ? TCAP / NTHREADS : 1;
+  static constexpr int HCAP = OSGPU_PAD_EY ? 64 : 96;  // CTA-wide list of pieces in halo cells (top of the buffer)
+  static constexpr int TCAP = FAST ? (((BUF_WORDS - NWARP * (XMIN * XW + QWORDS) - HCAP * XW) / NC) & ~31) : (1 << 30);
+  static constexpr int NROUND = FAST ? (TCAP + NTHREADS - 1) / NTHREADS : 1;
   static_assert(NROUND <= 16, "one mbarrier (and one phase bit) per staged round");
   static_assert(!FAST || TCAP < 4096, "queue entries keep the slot in 12 bits");
   static constexpr int NACC = 3 * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
@@ -639,14 +642,31 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           const int ib = (np > 0) ? min(cs[c + 1], pb) : 0;
           int id = heads[c];
           if (id) heads[c] = 0;
-          if (i < ib || id) {
+          // -- 3. pieces in halo cells (owned by a neighbouring tile) follow as extra jobs of the
+          // first threads, one piece each, through the same accumulate-and-flush code ------------
+          const int nh = OSGPU_HALO_JOBS ? min(s_nh, P::HCAP) : 0;
+          int he = tid;  // next halo piece of this thread
+          bool own = true;
+          for (;;) {
+            int pc = 0;
+            if (own) {
+              if (!(i < ib || id)) { own = false; continue; }
+            } else {
+              if (he >= nh) break;
+              pc = (int)hl[NC * P::HCAP + he];
+            }
             T acc[P::NACC];
 #pragma unroll
             for (int k = 0; k < P::NACC; k++) acc[k] = T(0);
-            while (i < ib || id) {
+            bool halo = !own;
+            while (i < ib || id || halo) {
               const T *src;
               int st;
-              if (i < ib) {  // a trajectory parked in its staged slot
+              if (halo) {      // a piece in a halo cell
+                src = hl + he;
+                st = P::HCAP;
+                halo = false;
+              } else if (i < ib) {  // a trajectory parked in its staged slot
                 src = buf + P::slot(i - pa);
                 st = 32;
                 i++;
@@ -669,15 +689,22 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               });
             }
             int lc[3];
-            lc[0] = c % G::TX;
-            lc[1] = (c / G::TX) % G::TY;
-            lc[2] = c / (G::TX * G::TY);
+            if (own) {
+              lc[0] = c % G::TX;
+              lc[1] = (c / G::TX) % G::TY;
+              lc[2] = c / (G::TX * G::TY);
+              own = false;
+            } else {
+#pragma unroll
+              for (int d = 0; d < 3; d++) lc[d] = ((pc >> (5 * d)) & 31) - 1;  // cell coordinates -1..T
+              he += NTHREADS;
+            }
             T *pj = jt + jtile_base<DIM, ORDER, T>(lc);
             flush_stencil<DIM, ORDER, T, P>(acc, pj);
           }
         }
+#if !OSGPU_HALO_JOBS
         if constexpr (P::FAST) {
-          // -- 3. pieces in halo cells (owned by a neighbouring tile): straight into the J tile --
           const int nh = min(s_nh, P::HCAP);
           for (int e = tid; e < nh; e += NTHREADS) {
             Seg<DIM, T> sg;
@@ -694,6 +721,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             deposit_segment<DIM, ORDER, T>(sg, q, jt, a.k, atomic_add);
           }
         }
+#endif
         qa = qb;
         if (more) {
           __syncthreads();  // the next piece reuses the buffer

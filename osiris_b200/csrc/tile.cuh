@@ -14,6 +14,14 @@ namespace pic {
 
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+#ifndef OSGPU_PAD_EY
+#define OSGPU_PAD_EY 1
+#endif
+// smallest row count >= ey whose plane pitch (row_words * rows, in 4-byte banks) is 8..24 mod 32
+constexpr int pad_tile_rows(int row_words, int ey) {
+  return ((row_words * ey) % 32 >= 8 && (row_words * ey) % 32 <= 24) ? ey : pad_tile_rows(row_words, ey + 1);
+}
+
 template <int DIM, int ORDER, typename T> struct Tile {
   using S = Stencil<ORDER>;
   static constexpr int NP = S::NP, LP = S::LP;
@@ -22,9 +30,14 @@ template <int DIM, int ORDER, typename T> struct Tile {
   static constexpr int TZ = (DIM == 2) ? 1 : 4;
   static constexpr int NCELL = TX * TY * TZ;  // 256 in both geometries
   // E/B tile: interpolation points l+LP-1 .. l+UP for every local cell l in [0,T)
-  static constexpr int EX = TX + NP, EY = TY + NP, EZ = (DIM == 3) ? TZ + NP : 1;
+  static constexpr int EX = TX + NP, EZ = (DIM == 3) ? TZ + NP : 1;
   // inner extent padded so a TMA box row is a multiple of 16 bytes
   static constexpr int EXP = round_up(EX, 16 / (int)sizeof(T));
+  // rows of the box: in 3D padded until the plane pitch is 8..24 banks (mod 32) away from a
+  // multiple of the bank count.  The particles of a warp sit in a few consecutive cells of one row;
+  // those whose half-cell shift selects the plane below would otherwise read the banks of their
+  // neighbours (3D quadratic: 12 x 11 words = 4 banks; measured 1.35 wavefronts per load)
+  static constexpr int EY = (DIM == 2 || !OSGPU_PAD_EY) ? TY + NP : pad_tile_rows(EXP * (int)sizeof(T) / 4, TY + NP);
   static constexpr int EVOL = EXP * EY * EZ;
   // per-component stride keeps every TMA destination 128-byte aligned
   static constexpr int ESTRIDE = round_up(EVOL * (int)sizeof(T), 128) / (int)sizeof(T);

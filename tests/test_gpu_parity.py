@@ -260,3 +260,41 @@ def test_continuity_at_scale(built):
     scale = np.abs(div[inner]).max()
     assert np.abs(res[1:-1, 1:-1]).max() < 2e-4 * scale, np.abs(res[1:-1, 1:-1]).max() / scale
     sim.close()
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_energy_history_long_run(built, prec):
+    """HIST/par_ene + HIST/fld_ene of a warm periodic plasma (the decks/test-style case, config 1 of
+    BASELINE.json: 2D, quadratic splines, uth = 0.1) over 200 steps on the device against the same
+    200 oracle steps: the two energy histories agree, and the total energy is conserved to the
+    level the reference's own explicit scheme conserves it (no secular drift beyond 1 %)."""
+    from osiris_b200.loads import lattice_species
+    from osiris_b200.simulation import Simulation
+    dim, order, nx, dx = 2, 2, [32, 32], [0.1, 0.1]
+    dt = 0.07
+    dt_ = np.float32 if prec == "f32" else np.float64
+    part = lattice_species(nx, [2, 2], dt_, rqm=-1.0, uth=(0.1, 0.1, 0.1), seed=7)
+    sim = Simulation(dim, order, nx, dx, dt, precision=prec)
+    sp = sim.add_species("electrons", -1.0, 4 * part["q"].shape[0])
+    sp.upload(part["ix"], part["x"], part["p"], part["q"])
+    ora = OracleSim(dim, order, nx, dx, dt, precision=prec)
+    ora.add_species(-1.0, part["ix"], part["x"], part["p"], part["q"])
+    nsteps = 200
+    kin, fld, kin_r, fld_r = [], [], [], []
+    for _ in range(nsteps):
+        kin.append(float(sim.iter(1)[0]))
+        fld.append(float(sim.emf.energy().sum()))
+        kin_r.append(float(ora.iter(1)[0]))
+        fld_r.append(float(ora.field_energy().sum()))
+    kin, fld, kin_r, fld_r = map(np.array, (kin, fld, kin_r, fld_r))
+    dvol = float(np.prod(dx))
+    # par_ene = rqm * dvol * sum(q u^2/(gamma+1)) (spec/os-spec-define.f03:1030-1086); rqm = -1, q < 0
+    par, par_r = -dvol * kin, -dvol * kin_r
+    tot, tot_r = par + fld, par_r + fld_r
+    ktol, ftol = (2e-5, 1e-3) if prec == "f32" else (1e-10, 1e-7)
+    assert np.abs(par / par_r - 1).max() < ktol, np.abs(par / par_r - 1).max()
+    assert np.abs(fld - fld_r).max() < ftol * fld_r.max(), np.abs(fld - fld_r).max() / fld_r.max()
+    assert np.abs(tot / tot_r - 1).max() < ktol * 5
+    assert abs(tot[-1] / tot[0] - 1) < 1e-2 and abs(tot_r[-1] / tot_r[0] - 1) < 1e-2
+    assert fld[-1] > 0 and fld.max() < 0.2 * par[0]  # thermal fluctuation level, no numerical heating blow-up
+    sim.close()

@@ -187,7 +187,8 @@ def main():
     ap.add_argument("--workload", default="uniform3d")
     ap.add_argument("--prec", default="f32")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU box (debug only)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks per species the host hands over in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -307,9 +308,10 @@ def main():
             "roofline": roof, "clocks": clocks, "gpu_launches": int(launches)}
 
     # ---- end to end through the C ABI with HOST buffers (N = 1) -----------------------------
-    if world == 1 and args.e2e_steps > 0 and rank == 0:
-        line["e2e"] = e2e_run(sim, lib, w, nx, host_parts, args.e2e_steps, dt_)
+    emf_shape = sim.emf_shape
     sim.close()
+    if world == 1 and args.e2e_steps > 0 and rank == 0:
+        line["e2e"] = e2e_run(lib, w, nx, host_parts, args.e2e_steps, dt_, args.prec, emf_shape, args.e2e_chunks)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -329,40 +331,56 @@ def main():
     return 0
 
 
-def e2e_run(sim, lib, w, nx, host_parts, nsteps, dt_):
+def e2e_run(lib, w, nx, host_parts, nsteps, dt_, prec, emf_shape, nchunk):
     """Same metric through the reference-facing call sequence with HOST buffers: every step copies
     the particle and field arrays host -> device (pinned memory), runs the step, and copies them
-    back -- what a drop-in at the pusher/solver boundary costs when nothing stays resident."""
-    import ctypes as C
+    back -- what a drop-in at the pusher/solver boundary costs when nothing stays resident.
+
+    The host hands the particles over in `nchunk` chunks per species, as the reference hands them
+    to its pusher one thread chunk at a time (spec/os-spec-vpush.f03:380-397): chunk k is uploaded,
+    pushed (its current added to J), wrapped and queued for download while chunk k+1 uploads, so
+    both PCIe directions are busy.  Then J guard cells, Yee, and the fields come back.  The phases
+    are the ones osgpu_step runs, per species (SURVEY.md 8b plug points)."""
+    from osiris_b200.simulation import Simulation
     L = lib.load()
-    pins = []
-    for part in host_parts:
+    nsp = len(host_parts)
+    sim = Simulation(w["dim"], w["order"], nx, w["dx"], w["dt"], precision=prec, nspecies=nsp * nchunk, add_tag=False)
+    pins, chunks = [], []
+    for si, part in enumerate(host_parts):
         d = {}
         for k, v in part.items():
             a = lib.pinned_empty(v.shape, v.dtype)
             a[...] = v
             d[k] = a
         pins.append(d)
-    e = lib.pinned_empty(sim.emf_shape, dt_)
-    b = lib.pinned_empty(sim.emf_shape, dt_)
+        n = d["q"].shape[0]
+        edge = (16, 16) if w["dim"] == 2 else (8, 8, 4)  # cell tiles (csrc/tile.cuh); every tile keeps 32 spare slots
+        ntile = int(np.prod([-(-nx[i] // edge[i]) for i in range(w["dim"])]))
+        for k in range(nchunk):
+            lo, hi = n * k // nchunk, n * (k + 1) // nchunk
+            sp = sim.add_species(f"s{si}c{k}", w["species"][si]["rqm"], int((hi - lo) * 1.25) + 48 * ntile + 65536)
+            chunks.append((sp, d, lo, hi))
+    e = lib.pinned_empty(emf_shape, dt_)
+    b = lib.pinned_empty(emf_shape, dt_)
     e[...] = 0
     b[...] = 0
     h2d = sum(sum(a.nbytes for a in d.values()) for d in pins) + e.nbytes + b.nbytes
     d2h = h2d
-    ene = np.zeros(max(1, len(pins)), np.float64)
 
     def one():
         sim.emf.upload(e, b)
-        for sp, d in zip(sim.part.species, pins):
-            lib.check(L.osgpu_species_upload(sim._h, sp.sp_id, d["q"].shape[0], lib.ptr(d["ix"]), lib.ptr(d["x"]),
-                                             lib.ptr(d["p"]), lib.ptr(d["q"]), None))
-        lib.check(L.osgpu_step(sim._h, 1, ene.ctypes.data_as(C.POINTER(C.c_double))))
-        for sp, d in zip(sim.part.species, pins):
-            n = sp.num_par
-            assert n == d["q"].shape[0]
-            lib.check(L.osgpu_species_download(sim._h, sp.sp_id, lib.ptr(d["ix"]), lib.ptr(d["x"]), lib.ptr(d["p"]),
-                                               lib.ptr(d["q"]), None))
+        sim.emf.update_boundary()
+        sim.jay.zero()
+        for sp, d, lo, hi in chunks:
+            lib.check(L.osgpu_species_upload(sim._h, sp.sp_id, hi - lo, lib.ptr(d["ix"][lo:hi]), lib.ptr(d["x"][lo:hi]),
+                                             lib.ptr(d["p"][lo:hi]), lib.ptr(d["q"][lo:hi]), None))
+            sp.push()
+            sp.update_boundary()
+            sp.fill_data_async(d["ix"][lo:hi], d["x"][lo:hi], d["p"][lo:hi], d["q"][lo:hi])
+        sim.jay.update_boundary()
+        sim.emf.advance()
         lib.check(L.osgpu_fields_download(sim._h, lib.ptr(e), lib.ptr(b)))
+        sim.sync()
 
     one()  # warm-up
     t0 = time.perf_counter()
@@ -370,15 +388,19 @@ def e2e_run(sim, lib, w, nx, host_parts, nsteps, dt_):
         one()
     el = time.perf_counter() - t0
     npart = sum(d["q"].shape[0] for d in pins)
+    assert sum(sp.num_par for sp, _, _, _ in chunks) == npart
+    sim.close()
     for d in pins:
         for a in d.values():
             lib.pinned_free(a)
     lib.pinned_free(e)
     lib.pinned_free(b)
     return {"value": npart * nsteps / el, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "steps": nsteps, "ms_per_step": 1e3 * el / nsteps,
-            "path": "osgpu_fields_upload + osgpu_species_upload + osgpu_step + osgpu_species_download + "
-                    "osgpu_fields_download, pinned host arrays"}
+            "steps": nsteps, "ms_per_step": 1e3 * el / nsteps, "chunks_per_species": nchunk,
+            "path": "per step: osgpu_fields_upload, osgpu_emf_update_boundary, osgpu_current_zero, per chunk "
+                    "[osgpu_species_upload, osgpu_species_push, osgpu_species_update_boundary, "
+                    "osgpu_species_download_async], osgpu_current_update_boundary, osgpu_emf_advance, "
+                    "osgpu_fields_download, osgpu_sync; pinned host arrays"}
 
 
 if __name__ == "__main__":

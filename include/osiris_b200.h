@@ -108,6 +108,14 @@ int64_t osgpu_species_count(osgpu_sim *sim, int sp_id);
 int osgpu_species_download(osgpu_sim *sim, int sp_id, int32_t *ix, void *x, void *p, void *q,
                            int64_t *tag);
 
+/* The same without the wait: returns once the gather and the device -> host copies are queued
+ * (the copies run on a second stream); the arrays are valid after osgpu_sync().  Together with the
+ * per-species phases below this lets a host stream one species -- or one chunk of a species, the way
+ * the reference calls its pusher once per thread chunk (spec/os-spec-vpush.f03:380-397) -- after the
+ * other: the download of one overlaps the upload of the next. */
+int osgpu_species_download_async(osgpu_sim *sim, int sp_id, int32_t *ix, void *x, void *p, void *q,
+                                 int64_t *tag);
+
 /* ---- fields: t_emf%e, t_emf%b, t_current%pf(1) ------------------------------------------ */
 int osgpu_fields_upload(osgpu_sim *sim, const void *e, const void *b);
 int osgpu_fields_download(osgpu_sim *sim, void *e, void *b);     /* emf/os-emf.f03:1158-1184 */
@@ -125,6 +133,14 @@ int osgpu_step(osgpu_sim *sim, int nsteps, double *ene_kin);
 int osgpu_emf_update_boundary(osgpu_sim *sim);     /* emf/boundary/os-emf-boundary.f90:723-830 */
 int osgpu_advance_deposit(osgpu_sim *sim, double *ene_kin); /* particles/os-particles.f03:1362 */
 int osgpu_particles_update_boundary(osgpu_sim *sim); /* spec/os-spec-boundary.f03:1099-1232   */
+/* the two particle phases for ONE species, the granularity of the reference's own plug points:
+ * osgpu_current_zero = jay%pf%zero() (particles/os-particles.f03:1396-1410), osgpu_species_push =
+ * push_species (spec/os-species.f03:1461-1520; the species' current is ADDED to J),
+ * osgpu_species_update_boundary = update_boundary_species (spec/os-spec-boundary.f03:1099-1232).
+ * osgpu_advance_deposit == current_zero + species_push for every species. */
+int osgpu_current_zero(osgpu_sim *sim);
+int osgpu_species_push(osgpu_sim *sim, int sp_id);
+int osgpu_species_update_boundary(osgpu_sim *sim, int sp_id);
 int osgpu_sort(osgpu_sim *sim);                      /* spec/os-species.f03:269-332           */
 int osgpu_current_update_boundary(osgpu_sim *sim); /* current/os-current-define.f03:683-727 */
 int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-482 (Yee)   */

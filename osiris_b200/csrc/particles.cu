@@ -34,30 +34,73 @@ __device__ __forceinline__ bool locate(const int *ix, int dim, const Tiling &tl,
   return ok;
 }
 
+// linear cell inside the tile, the order the push kernel keeps a tile sorted in (push.cu: linear_cell)
+__device__ __forceinline__ int tile_cell_index(int cell, const Tiling &tl) {
+  return cell_l(cell, 0) + tl.T[0] * (cell_l(cell, 1) + tl.T[1] * cell_l(cell, 2));
+}
+
+// Upload = counting sort by (tile, cell): the buffer comes out the way the push kernel leaves it,
+// every tile sorted by cell with its cell offsets known, so the first push after an upload already
+// runs the per-cell register accumulation (an unsorted tile sends every particle through the
+// piece lists).  Pass 1: particles per cell.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    count_kernel(AosParticles<T> in, long long np, int dim, Tiling tl, Grid g, int *tile_cnt, int *errflag) {
+    count_kernel(AosParticles<T> in, long long np, int dim, Tiling tl, Grid g, int *cell_cnt, int *errflag) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np;
        i += (long long)gridDim.x * blockDim.x) {
     int ix[3] = {1, 1, 1};
     for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d];
     int t, c;
-    if (locate(ix, dim, tl, g.nx, &t, &c)) atomicAdd(&tile_cnt[t], 1);
+    if (locate(ix, dim, tl, g.nx, &t, &c)) atomicAdd(&cell_cnt[(size_t)t * TILE_NCELL + tile_cell_index(c, tl)], 1);
     else atomicOr(errflag, ERRF_BAD_CELL);
   }
 }
 
+// Pass 2, one CTA per tile: cell counts -> cell offsets (exclusive scan), tile count; the counts
+// are cleared and serve as the scatter cursors of pass 3.
+__global__ void __launch_bounds__(TILE_NCELL)
+    cell_scan_kernel(int *cell_cnt, int *cell_start, int *tile_cnt, int *tile_nsorted) {
+  __shared__ int s_warp[TILE_NCELL / 32];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int v = cell_cnt[(size_t)t * TILE_NCELL + tid];
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < TILE_NCELL / 32; w++) {
+    const int u = s_warp[w];
+    if (w < wid) base += u;
+    tot += u;
+  }
+  cell_start[(size_t)t * (TILE_NCELL + 1) + tid] = base + inc - v;
+  cell_cnt[(size_t)t * TILE_NCELL + tid] = 0;
+  if (tid == 0) {
+    cell_start[(size_t)t * (TILE_NCELL + 1) + TILE_NCELL] = tot;
+    tile_cnt[t] = tot;
+    tile_nsorted[t] = tot;
+  }
+}
+
+// Pass 3: every particle to tile_off[tile] + cell_start[tile][cell] + (its turn inside the cell)
 template <typename T>
 __global__ void __launch_bounds__(256)
     scatter_kernel(AosParticles<T> in, long long np, long long tag_base, int dim, Tiling tl, Grid g,
-                   const int *tile_off, int *cursor, SpeciesView<T> sp) {
+                   const int *tile_off, const int *cell_start, int *cursor, SpeciesView<T> sp) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np;
        i += (long long)gridDim.x * blockDim.x) {
     int ix[3] = {1, 1, 1};
     for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d];
     int t, c;
     if (!locate(ix, dim, tl, g.nx, &t, &c)) continue;
-    const long long s = (long long)tile_off[t] + atomicAdd(&cursor[t], 1);
+    const int lc = tile_cell_index(c, tl);
+    const long long s = (long long)tile_off[t] + cell_start[(size_t)t * (TILE_NCELL + 1) + lc] +
+                        atomicAdd(&cursor[(size_t)t * TILE_NCELL + lc], 1);
     for (int d = 0; d < dim; d++) sp.r(d, s) = in.x[dim * i + d];
     for (int d = 0; d < 3; d++) sp.r(dim + d, s) = in.p[3 * i + d];
     sp.r(dim + 3, s) = in.q[i];
@@ -262,18 +305,18 @@ static int blocks_for(long long n) {
 }
 
 template <typename T>
-int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *tile_cnt,
-              int *errflag, cudaStream_t st, long long *launches) {
-  if (np == 0) return OSGPU_OK;
-  count_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, g.dim, tl, g, tile_cnt, errflag);
-  LAUNCHED(1);
+int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *cell_cnt,
+              int *cell_start, int *tile_cnt, int *tile_nsorted, int *errflag, cudaStream_t st, long long *launches) {
+  if (np > 0) count_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, g.dim, tl, g, cell_cnt, errflag);
+  cell_scan_kernel<<<tl.ntile, TILE_NCELL, 0, st>>>(cell_cnt, cell_start, tile_cnt, tile_nsorted);
+  LAUNCHED(2);
 }
 template <typename T>
 int bin_scatter(const AosParticles<T> &in, long long np, long long tag_base, const Grid &g, const Tiling &tl,
-                const int *tile_off, int *cursor, const SpeciesView<T> &sp, cudaStream_t st,
+                const int *tile_off, const int *cell_start, int *cursor, const SpeciesView<T> &sp, cudaStream_t st,
                 long long *launches) {
   if (np == 0) return OSGPU_OK;
-  scatter_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, tag_base, g.dim, tl, g, tile_off, cursor, sp);
+  scatter_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, tag_base, g.dim, tl, g, tile_off, cell_start, cursor, sp);
   LAUNCHED(1);
 }
 template <typename T>
@@ -327,10 +370,10 @@ int movers_unpack(const uint32_t *buf, int nrec, const Grid &g, int axis, int ad
 }
 
 #define INST(T)                                                                                               \
-  template int bin_count<T>(const AosParticles<T> &, long long, const Grid &, const Tiling &, int *, int *,    \
+  template int bin_count<T>(const AosParticles<T> &, long long, const Grid &, const Tiling &, int *, int *, int *, int *, int *,    \
                             cudaStream_t, long long *);                                                       \
   template int bin_scatter<T>(const AosParticles<T> &, long long, long long, const Grid &, const Tiling &,     \
-                              const int *, int *, const SpeciesView<T> &, cudaStream_t, long long *);          \
+                              const int *, const int *, int *, const SpeciesView<T> &, cudaStream_t, long long *); \
   template int gather_download<T>(const SpeciesView<T> &, const int *, const int *, const long long *,         \
                                   const Grid &, const Tiling &, int *, T *, T *, T *, long long *, int,        \
                                   cudaStream_t, long long *);                                                 \

@@ -15,12 +15,15 @@ template <typename T> struct AosParticles {
   const long long *tag;  // may be null
 };
 
+// upload = counting sort by (tile, cell).  cell_cnt: [ntile][TILE_NCELL] zeroed scratch (counts, then
+// scatter cursors); cell_start: [ntile][TILE_NCELL + 1] offsets; tile_cnt / tile_nsorted: per tile
 template <typename T>
-int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *tile_cnt,
-              int *errflag, cudaStream_t st, long long *launches);
+int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *cell_cnt,
+              int *cell_start, int *tile_cnt, int *tile_nsorted, int *errflag, cudaStream_t st, long long *launches);
 template <typename T>
 int bin_scatter(const AosParticles<T> &in, long long np, long long tag_base, const Grid &g, const Tiling &tl,
-                const int *tile_off, int *cursor, const SpeciesView<T> &sp, cudaStream_t st, long long *launches);
+                const int *tile_off, const int *cell_start, int *cursor, const SpeciesView<T> &sp, cudaStream_t st,
+                long long *launches);
 template <typename T>
 int gather_download(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const long long *out_off,
                     const Grid &g, const Tiling &tl, int *oix, T *ox, T *op, T *oq, long long *otag, int by_tag,

@@ -52,6 +52,11 @@ struct SimBase {
   virtual int sort() = 0;
   virtual int current_update_boundary() = 0;
   virtual int emf_advance() = 0;
+  virtual int current_zero() = 0;
+  virtual int species_push(int id) = 0;
+  virtual int species_update_boundary(int id) = 0;
+  virtual int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) = 0;
+  virtual int sync_all() = 0;
   virtual int current_set_smooth(const int *order, int max_order, const void *scoef) = 0;
   virtual int current_smooth() = 0;
   virtual int field_energy6(double *out6) = 0;
@@ -85,13 +90,18 @@ template <typename T> struct Sim final : SimBase {
     int *tile_nsorted = nullptr;  // leading particles of each tile that are sorted by cell
     int *cell_start = nullptr;    // [ntile][TILE_NCELL + 1] cell offsets inside the sorted range
     int *tile_counter = nullptr;  // work counter of the persistent push CTAs
+    int *cell_cur = nullptr;      // [ntile][TILE_NCELL] counts / cursors of the upload's counting sort (on first use)
     int max_range = 0;            // widest tile slot range of the current layout
     MoverView<T> mv;
     void *mvmem = nullptr;
     double *d_ene = nullptr;
     bool movers_pending = false;
+    char *dl_stage = nullptr;  // device staging of asynchronous downloads (kept, grown on demand)
+    size_t dl_cap = 0;
   };
   std::vector<Species> sp;
+  cudaStream_t st_d2h = nullptr;  // device -> host copies of species_download_async
+  cudaEvent_t ev_dl;
 
   int *d_err = nullptr;     // device error flags
   int *d_cnt = nullptr;     // small device scratch (send/recv counters)
@@ -156,6 +166,8 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &e : ev) OSGPU_CUDA(cudaEventCreate(&e));
     for (auto &e : ev_sm) OSGPU_CUDA(cudaEventCreate(&e));
+    OSGPU_CUDA(cudaStreamCreateWithFlags(&st_d2h, cudaStreamNonBlocking));
+    OSGPU_CUDA(cudaEventCreateWithFlags(&ev_dl, cudaEventDisableTiming));
 
     g.dim = dim;
     for (int d = 0; d < 3; d++) {
@@ -404,10 +416,18 @@ template <typename T> struct Sim final : SimBase {
           break;
         }
       }
-      cudaMemsetAsync(s.tile_cnt, 0, sizeof(int) * tl.ntile, st);
       cudaMemsetAsync(s.mv.count, 0, sizeof(int), st);
       s.movers_pending = false;
-      if ((rc = bin_count<T>(in, np, g, tl, s.tile_cnt, d_err, st, &launches)) != OSGPU_OK) break;
+      // counting sort by (tile, cell): count, per-tile scan (cell offsets, tile counts), scatter
+      if (!s.cell_cur) {
+        if (cudaMalloc(&s.cell_cur, sizeof(int) * (size_t)tl.ntile * pic::TILE_NCELL) != cudaSuccess) {
+          set_error("cell cursor allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+          rc = OSGPU_ERR_CUDA;
+          break;
+        }
+      }
+      cudaMemsetAsync(s.cell_cur, 0, sizeof(int) * (size_t)tl.ntile * pic::TILE_NCELL, st);
+      if ((rc = bin_count<T>(in, np, g, tl, s.cell_cur, s.cell_start, s.tile_cnt, s.tile_nsorted, d_err, st, &launches)) != OSGPU_OK) break;
       std::vector<int> cnt(tl.ntile), off;
       if (cudaMemcpyAsync(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaStreamSynchronize(st) != cudaSuccess) {
@@ -418,10 +438,8 @@ template <typename T> struct Sim final : SimBase {
       if ((rc = check_err("species_upload")) != OSGPU_OK) break;
       if ((rc = layout_offsets(cnt, s.cap, &off, &s.max_range)) != OSGPU_OK) break;
       s.cur = 0;
-      cudaMemsetAsync(s.tile_nsorted, 0, sizeof(int) * tl.ntile, st);  // bin_scatter leaves tiles unsorted
       cudaMemcpyAsync(s.tile_off[0], off.data(), sizeof(int) * (tl.ntile + 1), cudaMemcpyHostToDevice, st);
-      cudaMemsetAsync(s.tile_arr, 0, sizeof(int) * tl.ntile, st);  // used as the scatter cursor
-      if ((rc = bin_scatter<T>(in, np, 0, g, tl, s.tile_off[0], s.tile_arr, s.v[0], st, &launches)) != OSGPU_OK) break;
+      if ((rc = bin_scatter<T>(in, np, 0, g, tl, s.tile_off[0], s.cell_start, s.cell_cur, s.v[0], st, &launches)) != OSGPU_OK) break;
       if (cudaStreamSynchronize(st) != cudaSuccess) {
         set_error("species upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         rc = OSGPU_ERR_CUDA;
@@ -486,6 +504,66 @@ template <typename T> struct Sim final : SimBase {
       }
     } while (0);
     return rc;
+  }
+
+  // fill_data without the wait: the gather runs on the handle's stream, the device -> host copies on
+  // a second stream behind it, and the call returns as soon as they are queued -- the host arrays are
+  // valid after sync_all().  A host that moves one species (or one chunk of particles, as the
+  // reference's own pusher is called per thread chunk, spec/os-spec-vpush.f03:380-397) after the
+  // other keeps both PCIe directions busy: this download overlaps the next upload.
+  int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) override {
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    Species &s = sp[id];
+    std::vector<int> cnt(tl.ntile);
+    OSGPU_CUDA(cudaMemcpyAsync(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile, cudaMemcpyDeviceToHost, st));
+    OSGPU_CUDA(cudaMemcpyAsync(h_pin + 8, s.mv.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OSGPU_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> ooff(tl.ntile + 1);
+    long long n = 0;
+    for (int t = 0; t < tl.ntile; t++) { ooff[t] = n; n += cnt[t]; }
+    const long long nmov = s.movers_pending ? h_pin[8] : 0;
+    const long long np = n + nmov;
+    if (np == 0) return OSGPU_OK;
+    const size_t bix = sizeof(int) * dim * np, bx = sizeof(T) * dim * np, bp = sizeof(T) * 3 * np, bq = sizeof(T) * np;
+    const size_t btag = tag ? sizeof(long long) * np : 0, boff = sizeof(long long) * (tl.ntile + 1);
+    const size_t al = 256;
+    auto up = [&](size_t v) { return (v + al - 1) / al * al; };
+    const size_t need = up(bix) + up(bx) + up(bp) + up(bq) + up(btag) + up(boff) + al;
+    if (need > s.dl_cap) {
+      OSGPU_CUDA(cudaStreamSynchronize(st_d2h));  // an earlier download may still read the old area
+      if (s.dl_stage) cudaFree(s.dl_stage);
+      s.dl_stage = nullptr;
+      s.dl_cap = 0;
+      OSGPU_CUDA(cudaMalloc(&s.dl_stage, need + need / 8));
+      s.dl_cap = need + need / 8;
+    } else {
+      // the area is reused: the previous download of this species must have left it
+      OSGPU_CUDA(cudaStreamWaitEvent(st, ev_dl, 0));
+    }
+    char *c = s.dl_stage;
+    int *oix = (int *)c; c += up(bix);
+    T *ox = (T *)c; c += up(bx);
+    T *op = (T *)c; c += up(bp);
+    T *oq = (T *)c; c += up(bq);
+    long long *otag = tag ? (long long *)c : nullptr; c += up(btag);
+    long long *doff = (long long *)c;
+    OSGPU_CUDA(cudaMemcpyAsync(doff, ooff.data(), boff, cudaMemcpyHostToDevice, st));  // (pageable: staged before return)
+    OSGPU_TRY(gather_download<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, doff, g, tl, oix, ox, op, oq, otag, 0, st, &launches));
+    if (nmov) OSGPU_TRY(movers_download<T>(s.mv, n, g, oix, ox, op, oq, otag, 0, st, &launches));
+    OSGPU_CUDA(cudaEventRecord(ev_dl, st));
+    OSGPU_CUDA(cudaStreamWaitEvent(st_d2h, ev_dl, 0));
+    OSGPU_CUDA(cudaMemcpyAsync(ix, oix, bix, cudaMemcpyDeviceToHost, st_d2h));
+    OSGPU_CUDA(cudaMemcpyAsync(x, ox, bx, cudaMemcpyDeviceToHost, st_d2h));
+    OSGPU_CUDA(cudaMemcpyAsync(p, op, bp, cudaMemcpyDeviceToHost, st_d2h));
+    OSGPU_CUDA(cudaMemcpyAsync(q, oq, bq, cudaMemcpyDeviceToHost, st_d2h));
+    if (tag) OSGPU_CUDA(cudaMemcpyAsync(tag, otag, btag, cudaMemcpyDeviceToHost, st_d2h));
+    OSGPU_CUDA(cudaEventRecord(ev_dl, st_d2h));  // (now marks "copies of the latest download done")
+    return OSGPU_OK;
+  }
+  int sync_all() override {
+    OSGPU_CUDA(cudaStreamSynchronize(st));
+    if (st_d2h) OSGPU_CUDA(cudaStreamSynchronize(st_d2h));
+    return OSGPU_OK;
   }
 
   // ---------------------------------------------------------------------------------------
@@ -600,50 +678,60 @@ template <typename T> struct Sim final : SimBase {
   }
 
   // ---------------------------------------------------------------------------------------
-  int advance_deposit(double *ene) override {
-    OSGPU_CUDA(cudaMemsetAsync(J.c[0], 0, sizeof(T) * 3 * g.vol, st));  // jay%pf(tid)%zero()
+  int current_zero() override {  // jay%pf(tid)%zero()
+    OSGPU_CUDA(cudaMemsetAsync(J.c[0], 0, sizeof(T) * 3 * g.vol, st));
+    return OSGPU_OK;
+  }
+
+  // push_species for one species (spec/os-species.f03:1461-1520): its current is ADDED to J
+  int species_push(int id) override {
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    Species &s = sp[id];
+    if (s.movers_pending) { set_error("species %d pushed twice without update_boundary", id); return OSGPU_ERR_INVALID; }
     // particles use dt rounded to their precision (dtcycle, spec/os-spec-vpush.f03:374)
     const double dtp = (double)(T)cfg.dt;
-    for (size_t i = 0; i < sp.size(); i++) {
-      Species &s = sp[i];
-      if (!s.created) continue;
-      if (s.movers_pending) { set_error("advance_deposit called twice without particles_update_boundary"); return OSGPU_ERR_INVALID; }
-      PushArgs<T> a;
-      a.spc = s.v[s.cur];
-      a.mv = s.mv;
-      a.mvc.base = s.mv.x[0]; a.mvc.stride = s.mv.cap; a.mvc.cell = s.mv.ix[0]; a.mvc.tag = s.mv.tag;
-      a.tile_off = s.tile_off[s.cur];
-      a.tile_cnt = s.tile_cnt;
-      a.tile_nsorted = s.tile_nsorted;
-      a.cell_start = s.cell_start;
-      a.tile_counter = s.tile_counter;
-      // persistent CTAs; each owns one scratch range (widest tile) carved from the idle buffer
-      int nblocks = std::min(tl.ntile, n_sm * push_bps);
-      while (nblocks > 1 && (long long)nblocks * s.max_range > s.cap) nblocks--;
-      const long long nscr = std::max<long long>((long long)nblocks * s.max_range, 32);
-      carve(s.mem[1 - s.cur], dim, nscr, &a.scc);
-      a.scr_rank = a.scc.cell + nscr;
-      a.scr_stride = s.max_range;
-      OSGPU_CUDA(cudaMemsetAsync(s.tile_counter, 0, sizeof(int), st));
-      for (int k = 0; k < 3; k++) a.J[k] = J.c[k];
-      a.g = g;
-      a.tl = tl;
-      a.k.tem = (T)(0.5 * dtp / (double)(T)s.rqm);
-      for (int d = 0; d < 3; d++) {
-        a.k.dt_dx[d] = (d < dim) ? (T)(dtp / cfg.dx[d]) : T(0);
-        a.k.jnorm[d] = (d < dim) ? (T)(cfg.dx[d] / dtp / (dim == 2 ? 2 : 3)) : T(0);
-      }
-      a.ene = s.d_ene;
-      a.errflag = d_err;
-      OSGPU_CUDA(cudaMemsetAsync(s.d_ene, 0, sizeof(double), st));
-      OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
-      OSGPU_CUDA(cudaEventRecord(ev[8], st));
-      OSGPU_TRY(launch_push_deposit<T>(dim, order, maps, a, nblocks, st));
-      OSGPU_CUDA(cudaEventRecord(ev[9], st));
-      push_events++;
-      launches += 1;
-      s.movers_pending = true;
+    PushArgs<T> a;
+    a.spc = s.v[s.cur];
+    a.mv = s.mv;
+    a.mvc.base = s.mv.x[0]; a.mvc.stride = s.mv.cap; a.mvc.cell = s.mv.ix[0]; a.mvc.tag = s.mv.tag;
+    a.tile_off = s.tile_off[s.cur];
+    a.tile_cnt = s.tile_cnt;
+    a.tile_nsorted = s.tile_nsorted;
+    a.cell_start = s.cell_start;
+    a.tile_counter = s.tile_counter;
+    // persistent CTAs; each owns one scratch range (widest tile) carved from the idle buffer
+    int nblocks = std::min(tl.ntile, n_sm * push_bps);
+    while (nblocks > 1 && (long long)nblocks * s.max_range > s.cap) nblocks--;
+    const long long nscr = std::max<long long>((long long)nblocks * s.max_range, 32);
+    carve(s.mem[1 - s.cur], dim, nscr, &a.scc);
+    a.scr_rank = a.scc.cell + nscr;
+    a.scr_stride = s.max_range;
+    OSGPU_CUDA(cudaMemsetAsync(s.tile_counter, 0, sizeof(int), st));
+    for (int k = 0; k < 3; k++) a.J[k] = J.c[k];
+    a.g = g;
+    a.tl = tl;
+    a.k.tem = (T)(0.5 * dtp / (double)(T)s.rqm);
+    for (int d = 0; d < 3; d++) {
+      a.k.dt_dx[d] = (d < dim) ? (T)(dtp / cfg.dx[d]) : T(0);
+      a.k.jnorm[d] = (d < dim) ? (T)(cfg.dx[d] / dtp / (dim == 2 ? 2 : 3)) : T(0);
     }
+    a.ene = s.d_ene;
+    a.errflag = d_err;
+    OSGPU_CUDA(cudaMemsetAsync(s.d_ene, 0, sizeof(double), st));
+    OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
+    OSGPU_CUDA(cudaEventRecord(ev[8], st));
+    OSGPU_TRY(launch_push_deposit<T>(dim, order, maps, a, nblocks, st));
+    OSGPU_CUDA(cudaEventRecord(ev[9], st));
+    push_events++;
+    launches += 1;
+    s.movers_pending = true;
+    return OSGPU_OK;
+  }
+
+  int advance_deposit(double *ene) override {
+    OSGPU_TRY(current_zero());
+    for (size_t i = 0; i < sp.size(); i++)
+      if (sp[i].created) OSGPU_TRY(species_push((int)i));
     if (ene) {
       for (size_t i = 0; i < sp.size(); i++)
         if (sp[i].created) OSGPU_CUDA(cudaMemcpyAsync(&ene[i], sp[i].d_ene, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -653,29 +741,29 @@ template <typename T> struct Sim final : SimBase {
   }
 
   // migrate (ranks > 1), wrap, and re-insert the particles that left their tile
-  int particles_update_boundary() override {
+  int species_update_boundary(int id) override {  // update_boundary_species (spec/os-spec-boundary.f03:1099-1232)
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    Species &s = sp[id];
+    if (!s.movers_pending) return OSGPU_OK;
     int wrap[3] = {0, 0, 0};
     for (int d = 0; d < dim; d++) wrap[d] = (neigh[2 * d] == cfg.rank && neigh[2 * d + 1] == cfg.rank);
-    for (size_t i = 0; i < sp.size(); i++) {
-      Species &s = sp[i];
-      if (!s.created || !s.movers_pending) continue;
-      if (multi) OSGPU_TRY(migrate(s));
-      OSGPU_TRY(movers_route<T>(s.mv, g, tl, wrap, s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, st, &launches));
-    }
+    if (multi) OSGPU_TRY(migrate(s));
+    OSGPU_TRY(movers_route<T>(s.mv, g, tl, wrap, s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, st, &launches));
     OSGPU_CUDA(cudaMemcpyAsync(h_pin, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
     OSGPU_CUDA(cudaStreamSynchronize(st));
     const int f = h_pin[0];
     if (f & ~ERRF_TILE_OVERFLOW) return check_err("particles_update_boundary");
-    if (f & ERRF_TILE_OVERFLOW) {
+    if (f & ERRF_TILE_OVERFLOW) {  // an arrival found its tile full: fresh layout with room for the arrivals
       OSGPU_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-      for (auto &s : sp)
-        if (s.created) OSGPU_TRY(do_relayout(s, true));
+      OSGPU_TRY(do_relayout(s, true));
     }
-    for (auto &s : sp) {
-      if (!s.created || !s.movers_pending) continue;
-      OSGPU_TRY(movers_insert<T>(s.mv, g, tl, s.tile_off[s.cur], s.tile_cnt, s.v[s.cur], st, &launches));
-      s.movers_pending = false;
-    }
+    OSGPU_TRY(movers_insert<T>(s.mv, g, tl, s.tile_off[s.cur], s.tile_cnt, s.v[s.cur], st, &launches));
+    s.movers_pending = false;
+    return OSGPU_OK;
+  }
+  int particles_update_boundary() override {
+    for (size_t i = 0; i < sp.size(); i++)
+      if (sp[i].created) OSGPU_TRY(species_update_boundary((int)i));
     return OSGPU_OK;
   }
 
@@ -794,7 +882,11 @@ template <typename T> struct Sim final : SimBase {
 
   int finalize() override {
     if (st) cudaStreamSynchronize(st);
+    if (st_d2h) cudaStreamSynchronize(st_d2h);
     for (auto &s : sp) {
+      if (s.dl_stage) cudaFree(s.dl_stage);
+      if (s.cell_cur) cudaFree(s.cell_cur);
+      s.dl_stage = nullptr; s.dl_cap = 0; s.cell_cur = nullptr;
       for (int k = 0; k < 2; k++) { cudaFree(s.mem[k]); cudaFree(s.tile_off[k]); }
       cudaFree(s.tile_cnt); cudaFree(s.tile_arr); cudaFree(s.mvmem); cudaFree(s.d_ene);
       cudaFree(s.tile_nsorted); cudaFree(s.cell_start); cudaFree(s.tile_counter);
@@ -936,10 +1028,13 @@ int osgpu_field_energy(osgpu_sim *h, double *out6) { H_CHECK(h); return h->impl-
 int osgpu_phase_times_ms(osgpu_sim *h, double *out6) { H_CHECK(h); return h->impl->phase_times(out6); }
 int64_t osgpu_launch_count(osgpu_sim *h) { return h ? h->impl->launches : 0; }
 void *osgpu_stream(osgpu_sim *h) { return h ? (void *)h->impl->st : nullptr; }
-int osgpu_sync(osgpu_sim *h) {
+int osgpu_sync(osgpu_sim *h) { H_CHECK(h); return h->impl->sync_all(); }
+int osgpu_current_zero(osgpu_sim *h) { H_CHECK(h); return h->impl->current_zero(); }
+int osgpu_species_push(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_push(id); }
+int osgpu_species_update_boundary(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_update_boundary(id); }
+int osgpu_species_download_async(osgpu_sim *h, int id, int32_t *ix, void *x, void *p, void *q, int64_t *tag) {
   H_CHECK(h);
-  OSGPU_CUDA(cudaStreamSynchronize(h->impl->st));
-  return OSGPU_OK;
+  return h->impl->species_download_async(id, ix, x, p, q, (long long *)tag);
 }
 void *osgpu_host_alloc(size_t bytes) {
   void *p = nullptr;

@@ -62,6 +62,10 @@ def load():
     L.osgpu_species_count.argtypes = [vp, C.c_int]
     L.osgpu_species_count.restype = C.c_int64
     L.osgpu_species_download.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.osgpu_species_download_async.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    L.osgpu_species_push.argtypes = [vp, C.c_int]
+    L.osgpu_species_update_boundary.argtypes = [vp, C.c_int]
+    L.osgpu_current_zero.argtypes = [vp]
     L.osgpu_fields_upload.argtypes = [vp, vp, vp]
     L.osgpu_fields_download.argtypes = [vp, vp, vp]
     L.osgpu_current_upload.argtypes = [vp, vp]
@@ -129,5 +133,6 @@ EXPORTS = [
     "osgpu_particles_update_boundary", "osgpu_sort", "osgpu_current_update_boundary", "osgpu_emf_advance",
     "osgpu_field_energy", "osgpu_phase_times_ms", "osgpu_launch_count", "osgpu_stream", "osgpu_sync",
     "osgpu_host_alloc", "osgpu_host_free", "osgpu_vadvance_deposit", "osgpu_current_set_smooth",
-    "osgpu_current_smooth",
+    "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
+    "osgpu_species_download_async",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

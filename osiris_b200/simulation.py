@@ -84,6 +84,21 @@ class Species:
             out = {k: v[o] for k, v in out.items()}
         return out
 
+    def push(self):
+        """push_species (spec/os-species.f03:1461-1520): advance + deposit this species alone; its
+        current is added to J (zero it first with sim.jay.zero())."""
+        check(self.sim._L.osgpu_species_push(self.sim._h, self.sp_id))
+
+    def update_boundary(self):
+        """update_boundary_species (spec/os-spec-boundary.f03:1099-1232)"""
+        check(self.sim._L.osgpu_species_update_boundary(self.sim._h, self.sp_id))
+
+    def fill_data_async(self, ix, x, p, q, tag=None):
+        """Queue the device -> host copy into the given (preferably page-locked) arrays and return;
+        they are valid after sim.sync().  Arrays must hold num_par particles."""
+        check(self.sim._L.osgpu_species_download_async(self.sim._h, self.sp_id, ptr(ix), ptr(x), ptr(p), ptr(q),
+                                                       ptr(tag)))
+
 
 class _Emf:
     """t_emf (emf/os-emf-define.f03:197-281)"""
@@ -133,6 +148,9 @@ class _Current:
 
     def update_boundary(self):
         check(self.sim._L.osgpu_current_update_boundary(self.sim._h))
+
+    def zero(self):
+        check(self.sim._L.osgpu_current_zero(self.sim._h))
 
     def set_smooth(self, smooth):
         """Hand setup_smooth's result (osiris_b200.smooth.Smooth) to the device; None switches it off."""

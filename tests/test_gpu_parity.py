@@ -298,3 +298,62 @@ def test_energy_history_long_run(built, prec):
     assert abs(tot[-1] / tot[0] - 1) < 1e-2 and abs(tot_r[-1] / tot_r[0] - 1) < 1e-2
     assert fld[-1] > 0 and fld.max() < 0.2 * par[0]  # thermal fluctuation level, no numerical heating blow-up
     sim.close()
+
+
+def test_per_species_phases_and_async_download(built):
+    """the per-species plug points (push_species / update_boundary_species) with the particles of
+    one species dealt to four device species as chunks, each uploaded, pushed, wrapped and
+    downloaded (asynchronously) in turn: same particles, same fields as the one-call step"""
+    from osiris_b200 import lib
+    from osiris_b200.simulation import Simulation
+    dim, order, prec, nx = 3, 2, "f32", SHAPES[3]
+    dx = DX[dim]
+    dt = 0.4 * min(dx) / np.sqrt(dim)
+    c = random_case(dim, order, prec, nx, 6, seed=21, umax=0.3, efield=0.05)
+    n = c["q"].shape[0]
+    nchunk = 4
+    bounds = [n * k // nchunk for k in range(nchunk + 1)]
+    ora = OracleSim(dim, order, nx, dx, dt, precision=prec, gc_emf=c["gc"], gc_jay=c["gc"])
+    ora.e[...] = c["e"]
+    ora.b[...] = c["b"]
+    ora.add_species(-1.0, c["ix"], c["x"], c["u"], c["q"])
+    sim = Simulation(dim, order, nx, dx, dt, precision=prec, nspecies=nchunk, gc_emf=c["gc"], gc_jay=c["gc"])
+    chunks = [sim.add_species(f"chunk{k}", -1.0, 2 * (bounds[k + 1] - bounds[k]) + 4096) for k in range(nchunk)]
+    out = dict(ix=lib.pinned_empty((n, dim), np.int32), x=lib.pinned_empty((n, dim), np.float32),
+               p=lib.pinned_empty((n, 3), np.float32), q=lib.pinned_empty((n,), np.float32),
+               tag=lib.pinned_empty((n,), np.int64))
+    for step in range(2):
+        src = dict(ix=c["ix"], x=c["x"], p=c["u"], q=c["q"]) if step == 0 else {k: out[k].copy() for k in ("ix", "x", "p", "q")}
+        tags = np.arange(n, dtype=np.int64) if step == 0 else out["tag"].copy()
+        if step == 0:
+            sim.emf.upload(c["e"], c["b"])
+        sim.emf.update_boundary()
+        sim.jay.zero()
+        for k, sp in enumerate(chunks):
+            sl = slice(bounds[k], bounds[k + 1])
+            sp.upload(src["ix"][sl], src["x"][sl], src["p"][sl], src["q"][sl], tag=tags[sl])
+            sp.push()
+            sp.update_boundary()
+            assert sp.num_par == bounds[k + 1] - bounds[k]
+            sp.fill_data_async(out["ix"][sl], out["x"][sl], out["p"][sl], out["q"][sl], out["tag"][sl])
+        sim.jay.update_boundary()
+        sim.emf.advance()
+        sim.sync()
+        ora.iter(1)
+        o = np.argsort(out["tag"], kind="stable")
+        r = ora.species[0]
+        assert np.array_equal(out["tag"][o], np.arange(n))
+        if step == 0:  # identical inputs: bit-exact particles
+            assert np.array_equal(out["ix"][o], r["ix"])
+            assert np.array_equal(out["x"][o], r["x"]) and np.array_equal(out["p"][o], r["p"])
+        else:          # fields differ by the J summation order after the first step
+            pos = out["ix"][o] + out["x"][o].astype(np.float64)
+            dd = np.abs(pos - (r["ix"] + r["x"].astype(np.float64)))
+            dd = np.minimum(dd, np.array(nx, np.float64) - dd)
+            assert dd.max() < 1e-4 and np.abs(out["p"][o] - r["p"]).max() < 1e-4
+        e, b = sim.emf.fill_data()
+        s = max(np.abs(ora.e).max(), np.abs(ora.b).max())
+        assert np.abs(e - ora.e).max() <= 1e-5 * s and np.abs(b - ora.b).max() <= 1e-5 * s
+    for a in out.values():
+        lib.pinned_free(a)
+    sim.close()

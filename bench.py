@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--prec", default="f32")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU box (debug only)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks per species the host hands over in the e2e leg")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks per species the host hands over in the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -367,13 +367,19 @@ def e2e_run(lib, w, nx, host_parts, nsteps, dt_, prec, emf_shape, nchunk):
     h2d = sum(sum(a.nbytes for a in d.values()) for d in pins) + e.nbytes + b.nbytes
     d2h = h2d
 
+    def begin(k):
+        sp, d, lo, hi = chunks[k]
+        sp.upload_begin(d["ix"][lo:hi], d["x"][lo:hi], d["p"][lo:hi], d["q"][lo:hi])
+
     def one():
+        begin(0)
         sim.emf.upload(e, b)
         sim.emf.update_boundary()
         sim.jay.zero()
-        for sp, d, lo, hi in chunks:
-            lib.check(L.osgpu_species_upload(sim._h, sp.sp_id, hi - lo, lib.ptr(d["ix"][lo:hi]), lib.ptr(d["x"][lo:hi]),
-                                             lib.ptr(d["p"][lo:hi]), lib.ptr(d["q"][lo:hi]), None))
+        for k, (sp, d, lo, hi) in enumerate(chunks):
+            sp.upload_end()
+            if k + 1 < len(chunks):
+                begin(k + 1)  # copies under the push of chunk k
             sp.push()
             sp.update_boundary()
             sp.fill_data_async(d["ix"][lo:hi], d["x"][lo:hi], d["p"][lo:hi], d["q"][lo:hi])
@@ -398,7 +404,7 @@ def e2e_run(lib, w, nx, host_parts, nsteps, dt_, prec, emf_shape, nchunk):
     return {"value": npart * nsteps / el, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "steps": nsteps, "ms_per_step": 1e3 * el / nsteps, "chunks_per_species": nchunk,
             "path": "per step: osgpu_fields_upload, osgpu_emf_update_boundary, osgpu_current_zero, per chunk "
-                    "[osgpu_species_upload, osgpu_species_push, osgpu_species_update_boundary, "
+                    "[osgpu_species_upload_begin (one chunk ahead), osgpu_species_upload_end, osgpu_species_push, osgpu_species_update_boundary, "
                     "osgpu_species_download_async], osgpu_current_update_boundary, osgpu_emf_advance, "
                     "osgpu_fields_download, osgpu_sync; pinned host arrays"}
 

@@ -102,6 +102,12 @@ int osgpu_species_create(osgpu_sim *sim, int sp_id, double rqm, int64_t np_max);
  * (spec/os-species.f03:1867-1894). */
 int osgpu_species_upload(osgpu_sim *sim, int sp_id, int64_t np, const int32_t *ix, const void *x,
                          const void *p, const void *q, const int64_t *tag);
+/* the same in two halves: _begin queues the host -> device copies on a copy stream and returns (the
+ * host arrays must stay untouched until _end returns), _end sorts the staged particles into the
+ * species' buffer.  osgpu_species_upload == _begin + _end + wait.  At most two uploads in flight. */
+int osgpu_species_upload_begin(osgpu_sim *sim, int sp_id, int64_t np, const int32_t *ix, const void *x,
+                               const void *p, const void *q, const int64_t *tag);
+int osgpu_species_upload_end(osgpu_sim *sim, int sp_id);
 int64_t osgpu_species_count(osgpu_sim *sim, int sp_id);
 /* device -> host AoS (fill_data target).  Arrays hold osgpu_species_count() particles, in device
  * (tile) order; tag (may be NULL) identifies them. */

@@ -59,6 +59,8 @@ def load():
     L.osgpu_finalize.argtypes = [vp]
     L.osgpu_species_create.argtypes = [vp, C.c_int, C.c_double, C.c_int64]
     L.osgpu_species_upload.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
+    L.osgpu_species_upload_begin.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
+    L.osgpu_species_upload_end.argtypes = [vp, C.c_int]
     L.osgpu_species_count.argtypes = [vp, C.c_int]
     L.osgpu_species_count.restype = C.c_int64
     L.osgpu_species_download.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
@@ -134,5 +136,5 @@ EXPORTS = [
     "osgpu_field_energy", "osgpu_phase_times_ms", "osgpu_launch_count", "osgpu_stream", "osgpu_sync",
     "osgpu_host_alloc", "osgpu_host_free", "osgpu_vadvance_deposit", "osgpu_current_set_smooth",
     "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
-    "osgpu_species_download_async",
+    "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -65,6 +65,18 @@ class Species:
         check(self.sim._L.osgpu_species_upload(self.sim._h, self.sp_id, q.shape[0], ptr(ix), ptr(x), ptr(p),
                                                ptr(q), ptr(tag)))
 
+    def upload_begin(self, ix, x, p, q, tag=None):
+        """Queue the host -> device copies and return; the arrays (contiguous, of the simulation's
+        precision, preferably page-locked) must stay untouched until upload_end()."""
+        dt = self.sim.dtype
+        assert ix.dtype == np.int32 and x.dtype == dt and p.dtype == dt and q.dtype == dt
+        assert all(a.flags.c_contiguous for a in (ix, x, p, q))
+        check(self.sim._L.osgpu_species_upload_begin(self.sim._h, self.sp_id, q.shape[0], ptr(ix), ptr(x), ptr(p),
+                                                     ptr(q), ptr(tag)))
+
+    def upload_end(self):
+        check(self.sim._L.osgpu_species_upload_end(self.sim._h, self.sp_id))
+
     @property
     def num_par(self):
         n = self.sim._L.osgpu_species_count(self.sim._h, self.sp_id)

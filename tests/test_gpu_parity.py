@@ -331,7 +331,9 @@ def test_per_species_phases_and_async_download(built):
         sim.jay.zero()
         for k, sp in enumerate(chunks):
             sl = slice(bounds[k], bounds[k + 1])
-            sp.upload(src["ix"][sl], src["x"][sl], src["p"][sl], src["q"][sl], tag=tags[sl])
+            sp.upload_begin(np.ascontiguousarray(src["ix"][sl]), np.ascontiguousarray(src["x"][sl]), np.ascontiguousarray(src["p"][sl]),
+                            np.ascontiguousarray(src["q"][sl]), tag=np.ascontiguousarray(tags[sl]))
+            sp.upload_end()
             sp.push()
             sp.update_boundary()
             assert sp.num_par == bounds[k + 1] - bounds[k]

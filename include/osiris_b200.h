@@ -159,6 +159,14 @@ int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-
  * -> filter_2d/filter_3d (vdf/os-vdf-smooth.f90:639-1105). */
 int osgpu_current_set_smooth(osgpu_sim *sim, const int32_t *order, int max_order, const void *scoef);
 int osgpu_current_smooth(osgpu_sim *sim);
+/* Field smoothing for the particles, el_mag_fld{ smooth_type = "stand" } (emf/os-emf.f03:425-443,
+ * 774-792): the particles interpolate e_part / b_part = smooth(e), smooth(b) with the t_smooth of
+ * t_emf (same order / scoef convention as above); the solver keeps the unsmoothed fields.  Needs
+ * gc_emf >= interpolation guard cells + order (emf/os-emf.f03:663-724).  Once set, osgpu_step
+ * refreshes e_part, b_part after emf%update_boundary; osgpu_emf_update_particle_fld is that phase
+ * alone (update_particle_fld_emf, emf/os-emf.f03:1065-1150). */
+int osgpu_emf_set_smooth(osgpu_sim *sim, const int32_t *order, int max_order, const void *scoef);
+int osgpu_emf_update_particle_fld(osgpu_sim *sim);
 /* field energy per component, interior cells: out6 = {E1,E2,E3,B1,B2,B3}
  * (emf/diagnostics/os-emf-diagnostics.f03:43-58); summed over this rank only */
 int osgpu_field_energy(osgpu_sim *sim, double *out6);

@@ -133,27 +133,45 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// All passes of the filter: src -> dst (src == dst allowed: in place), scratch planes tmp.  The
+// passes alternate between dst and tmp and are ordered so that the last one writes dst; with no
+// active axis dst is a copy of src.  Every Field3 is three contiguous component planes.
 template <typename T>
-int smooth_current(const Grid &g, Field3<T> jay, Field3<T> tmp, const SmoothBox &bx, const int *order,
-                   const SmoothCoef<T> *coef, cudaStream_t st, long long *launches) {
-  Field3<T> a = jay, b = tmp;
+int smooth_field(const Grid &g, Field3<T> src, Field3<T> dst, Field3<T> tmp, const SmoothBox &bx, const int *order,
+                 const SmoothCoef<T> *coef, cudaStream_t st, long long *launches) {
+  int npass = 0;
+  for (int ax = 0; ax < g.dim; ax++) npass += order[ax] > 0;
+  if (npass == 0) {
+    if (src.c[0] != dst.c[0])
+      OSGPU_CUDA(cudaMemcpyAsync(dst.c[0], src.c[0], sizeof(T) * 3 * g.vol, cudaMemcpyDeviceToDevice, st));
+    return OSGPU_OK;
+  }
+  const bool inplace = src.c[0] == dst.c[0];
+  // targets of pass k = 0..npass-1: ..., tmp, dst, tmp, dst (last = dst); in place the first target
+  // cannot be dst itself, so an odd pass count ends in tmp and is copied back
   const dim3 blk(128), grid((g.S[0] + 127) / 128, g.S[1], g.S[2]);
+  Field3<T> cur = src;
+  int k = 0;
+  bool to_dst = inplace ? false : ((npass & 1) == 1);
   for (int ax = 0; ax < g.dim; ax++) {
     if (order[ax] <= 0) continue;
-    Field3<const T> ca{{a.c[0], a.c[1], a.c[2]}};
-    smooth_axis_kernel<T><<<grid, blk, 0, st>>>(b, ca, g, bx, ax, order[ax], coef[ax]);
+    Field3<T> out = to_dst ? dst : tmp;
+    Field3<const T> ca{{cur.c[0], cur.c[1], cur.c[2]}};
+    smooth_axis_kernel<T><<<grid, blk, 0, st>>>(out, ca, g, bx, ax, order[ax], coef[ax]);
     *launches += 1;
-    std::swap(a, b);
+    cur = out;
+    to_dst = !to_dst;
+    k++;
   }
   OSGPU_CUDA(cudaGetLastError());
-  if (a.c[0] != jay.c[0])  // odd number of passes: the result sits in the scratch planes (contiguous)
-    OSGPU_CUDA(cudaMemcpyAsync(jay.c[0], a.c[0], sizeof(T) * 3 * g.vol, cudaMemcpyDeviceToDevice, st));
+  if (cur.c[0] != dst.c[0])
+    OSGPU_CUDA(cudaMemcpyAsync(dst.c[0], cur.c[0], sizeof(T) * 3 * g.vol, cudaMemcpyDeviceToDevice, st));
   return OSGPU_OK;
 }
-template int smooth_current<float>(const Grid &, Field3<float>, Field3<float>, const SmoothBox &, const int *,
-                                   const SmoothCoef<float> *, cudaStream_t, long long *);
-template int smooth_current<double>(const Grid &, Field3<double>, Field3<double>, const SmoothBox &, const int *,
-                                    const SmoothCoef<double> *, cudaStream_t, long long *);
+template int smooth_field<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>, const SmoothBox &, const int *,
+                                 const SmoothCoef<float> *, cudaStream_t, long long *);
+template int smooth_field<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>, const SmoothBox &, const int *,
+                                  const SmoothCoef<double> *, cudaStream_t, long long *);
 
 // ---------------------------------------------------------------------------------------------
 // Slab helpers.  A slab is the padded range [a0, a1] along `axis` times the full padded extent of

@@ -28,10 +28,11 @@ template <typename T> struct SmoothCoef {
 struct SmoothBox {
   int lo[3], hi[3];
 };
-// jay and tmp: three contiguous component planes each (c[1] = c[0] + vol, c[2] = c[0] + 2 vol)
+// every pass of the filter, src -> dst (src == dst: in place) through the scratch planes tmp; each
+// Field3 is three contiguous component planes (c[1] = c[0] + vol, c[2] = c[0] + 2 vol)
 template <typename T>
-int smooth_current(const Grid &g, Field3<T> jay, Field3<T> tmp, const SmoothBox &bx, const int *order,
-                   const SmoothCoef<T> *coef, cudaStream_t st, long long *launches);
+int smooth_field(const Grid &g, Field3<T> src, Field3<T> dst, Field3<T> tmp, const SmoothBox &bx, const int *order,
+                 const SmoothCoef<T> *coef, cudaStream_t st, long long *launches);
 template <typename T>
 int field_energy(const Grid &g, T *const *comps6, double *dev_out6, cudaStream_t st, long long *launches);
 

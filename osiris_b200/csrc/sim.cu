@@ -61,6 +61,8 @@ struct SimBase {
   virtual int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) = 0;
   virtual int sync_all() = 0;
   virtual int current_set_smooth(const int *order, int max_order, const void *scoef) = 0;
+  virtual int emf_set_smooth(const int *order, int max_order, const void *scoef) = 0;
+  virtual int emf_update_particle_fld() = 0;
   virtual int current_smooth() = 0;
   virtual int field_energy6(double *out6) = 0;
   virtual int phase_times(double *out6) = 0;
@@ -183,6 +185,12 @@ template <typename T> struct Sim final : SimBase {
   SmoothCoef<T> sm_coef[3];
   T *jtmp = nullptr;
   cudaEvent_t ev_sm[2];
+  // field smoothing for the particles (t_emf%smooth_type = "stand"): e_part, b_part
+  bool emf_smooth_on = false;
+  int em_order[3] = {0, 0, 0};
+  SmoothCoef<T> em_coef[3];
+  T *fld_part = nullptr;  // 6 planes
+  Field3<T> Ep, Bp;
   // device staging area of the host-array transfers (fill_data in both directions): kept between
   // calls and only ever grown, so a host that moves a species every step does not pay a multi-GB
   // cudaMalloc/cudaFree per transfer
@@ -334,7 +342,9 @@ template <typename T> struct Sim final : SimBase {
     const cuuint64_t gstr[2] = {(cuuint64_t)g.P0 * sizeof(T), (cuuint64_t)g.P0 * g.S[1] * sizeof(T)};
     const cuuint32_t es[3] = {1, 1, 1};
     for (int c = 0; c < 9; c++) {
-      T *base = (c < 3) ? E.c[c] : (c < 6 ? B.c[c - 3] : J.c[c - 6]);
+      // the particles interpolate e_part / b_part (== e, b unless field smoothing is on, emf/os-emf.f03:774-792)
+      const Field3<T> &ei = emf_smooth_on ? Ep : E, &bi = emf_smooth_on ? Bp : B;
+      T *base = (c < 3) ? ei.c[c] : (c < 6 ? bi.c[c - 3] : J.c[c - 6]);
       const int *bb = (c < 6) ? box : jbox;
       const cuuint32_t bx[3] = {(cuuint32_t)bb[0], (cuuint32_t)bb[1], (cuuint32_t)bb[2]};
       CUresult r = ((encode_fn)fn)(&maps.m[c],
@@ -777,8 +787,58 @@ template <typename T> struct Sim final : SimBase {
     }
     Field3<T> tmp{{jtmp, jtmp + g.vol, jtmp + 2 * g.vol}};
     OSGPU_CUDA(cudaEventRecord(ev_sm[0], st));
-    OSGPU_TRY(smooth_current<T>(g, J, tmp, bx, sm_order, sm_coef, st, &launches));
+    OSGPU_TRY(smooth_field<T>(g, J, J, tmp, bx, sm_order, sm_coef, st, &launches));
     OSGPU_CUDA(cudaEventRecord(ev_sm[1], st));
+    return OSGPU_OK;
+  }
+
+  // t_emf with smooth_type = "stand": order / scoef of its t_smooth, as for the current.  The guard
+  // cells must hold the smoothing order on top of what interpolation needs (emf/os-emf.f03:663-724).
+  int emf_set_smooth(const int *ord, int max_order, const void *scoef) override {
+    if (max_order < 0 || max_order > SMOOTH_ORDER_MAX) { set_error("smooth: max_order %d outside 0..%d", max_order, SMOOTH_ORDER_MAX); return OSGPU_ERR_INVALID; }
+    bool any = false;
+    for (int d = 0; d < dim; d++) {
+      if (ord[d] < 0 || ord[d] > max_order) { set_error("smooth: order(%d) = %d outside 0..max_order", d + 1, ord[d]); return OSGPU_ERR_INVALID; }
+      const int lo = std::max(min_gc_lower(order), 1) + ord[d], up = std::max(min_gc_upper(order), 2) + ord[d];
+      if (ord[d] > 0 && (cfg.gc_emf[0][d] < lo || cfg.gc_emf[1][d] < up)) {
+        set_error("field smoothing: axis %d needs field guard cells (%d,%d), has (%d,%d)", d + 1, lo, up, cfg.gc_emf[0][d], cfg.gc_emf[1][d]);
+        return OSGPU_ERR_INVALID;
+      }
+      any |= ord[d] > 0;
+    }
+    if (any && !scoef) { set_error("smooth: scoef is null"); return OSGPU_ERR_INVALID; }
+    const T *sc = static_cast<const T *>(scoef);
+    const int W = 2 * max_order + 1;
+    for (int d = 0; d < 3; d++) {
+      em_order[d] = (d < dim) ? ord[d] : 0;
+      for (int k = 0; k < 2 * SMOOTH_ORDER_MAX + 1; k++) em_coef[d].s[k] = T(0);
+      if (d < dim && sc)
+        for (int k = -max_order; k <= max_order; k++) em_coef[d].s[SMOOTH_ORDER_MAX + k] = sc[d * W + max_order + k];
+    }
+    if (any && !fld_part) {
+      OSGPU_CUDA(cudaMalloc(&fld_part, sizeof(T) * 6 * g.vol));
+      OSGPU_CUDA(cudaMemsetAsync(fld_part, 0, sizeof(T) * 6 * g.vol, st));
+      for (int k = 0; k < 3; k++) { Ep.c[k] = fld_part + k * g.vol; Bp.c[k] = fld_part + (3 + k) * g.vol; }
+    }
+    if (any && !jtmp) OSGPU_CUDA(cudaMalloc(&jtmp, sizeof(T) * 3 * g.vol));
+    if (any != emf_smooth_on) {
+      OSGPU_CUDA(cudaStreamSynchronize(st));  // a queued push still holds the old maps by value: harmless, but keep order simple
+      emf_smooth_on = any;
+      OSGPU_TRY(make_tensor_maps());
+    }
+    return OSGPU_OK;
+  }
+  // update_particle_fld (emf/os-emf.f03:1065-1150): e_part = e, b_part = b, smooth both
+  int emf_update_particle_fld() override {
+    if (!emf_smooth_on) return OSGPU_OK;
+    SmoothBox bx;
+    for (int d = 0; d < 3; d++) {
+      bx.lo[d] = (d < dim) ? g.gl[d] - cfg.gc_emf[0][d] : 0;
+      bx.hi[d] = (d < dim) ? g.gl[d] + g.nx[d] + cfg.gc_emf[1][d] - 1 : 0;
+    }
+    Field3<T> tmp{{jtmp, jtmp + g.vol, jtmp + 2 * g.vol}};
+    OSGPU_TRY(smooth_field<T>(g, E, Ep, tmp, bx, em_order, em_coef, st, &launches));
+    OSGPU_TRY(smooth_field<T>(g, B, Bp, tmp, bx, em_order, em_coef, st, &launches));
     return OSGPU_OK;
   }
 
@@ -929,6 +989,7 @@ template <typename T> struct Sim final : SimBase {
       const bool last = (n == nsteps - 1);
       OSGPU_CUDA(cudaEventRecord(ev[0], st));
       OSGPU_TRY(emf_update_boundary());
+      OSGPU_TRY(emf_update_particle_fld());
       OSGPU_CUDA(cudaEventRecord(ev[1], st));
       OSGPU_TRY(advance_deposit(nullptr));
       OSGPU_CUDA(cudaEventRecord(ev[2], st));
@@ -1001,6 +1062,8 @@ template <typename T> struct Sim final : SimBase {
     cudaFree(fld); cudaFree(d_err); cudaFree(d_cnt); cudaFree(d_fe);
     if (stage_mem) cudaFree(stage_mem);
     if (jtmp) cudaFree(jtmp);
+    if (fld_part) cudaFree(fld_part);
+    fld_part = nullptr;
     stage_mem = nullptr; stage_cap = 0; jtmp = nullptr;
     if (h_pin) cudaFreeHost(h_pin);
     if (h_ctl) cudaFreeHost(h_ctl);
@@ -1131,6 +1194,12 @@ int osgpu_current_set_smooth(osgpu_sim *h, const int *order, int max_order, cons
   return h->impl->current_set_smooth(order, max_order, scoef);
 }
 int osgpu_current_smooth(osgpu_sim *h) { H_CHECK(h); return h->impl->current_smooth(); }
+int osgpu_emf_set_smooth(osgpu_sim *h, const int *order, int max_order, const void *scoef) {
+  H_CHECK(h);
+  if (!order) { osgpu::set_error("smooth: order is null"); return OSGPU_ERR_INVALID; }
+  return h->impl->emf_set_smooth(order, max_order, scoef);
+}
+int osgpu_emf_update_particle_fld(osgpu_sim *h) { H_CHECK(h); return h->impl->emf_update_particle_fld(); }
 int osgpu_field_energy(osgpu_sim *h, double *out6) { H_CHECK(h); return h->impl->field_energy6(out6); }
 int osgpu_phase_times_ms(osgpu_sim *h, double *out6) { H_CHECK(h); return h->impl->phase_times(out6); }
 int64_t osgpu_launch_count(osgpu_sim *h) { return h ? h->impl->launches : 0; }

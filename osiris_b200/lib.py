@@ -74,9 +74,11 @@ def load():
     L.osgpu_current_download.argtypes = [vp, vp]
     L.osgpu_step.argtypes = [vp, C.c_int, dp]
     for name in ("osgpu_emf_update_boundary", "osgpu_particles_update_boundary", "osgpu_sort",
-                 "osgpu_current_update_boundary", "osgpu_emf_advance", "osgpu_sync", "osgpu_current_smooth"):
+                 "osgpu_current_update_boundary", "osgpu_emf_advance", "osgpu_sync", "osgpu_current_smooth",
+                 "osgpu_emf_update_particle_fld"):
         getattr(L, name).argtypes = [vp]
     L.osgpu_current_set_smooth.argtypes = [vp, vp, C.c_int, vp]
+    L.osgpu_emf_set_smooth.argtypes = [vp, vp, C.c_int, vp]
     L.osgpu_advance_deposit.argtypes = [vp, dp]
     L.osgpu_field_energy.argtypes = [vp, dp]
     L.osgpu_phase_times_ms.argtypes = [vp, dp]
@@ -137,4 +139,5 @@ EXPORTS = [
     "osgpu_host_alloc", "osgpu_host_free", "osgpu_vadvance_deposit", "osgpu_current_set_smooth",
     "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
+    "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -136,6 +136,21 @@ class _Emf:
     def advance(self):
         check(self.sim._L.osgpu_emf_advance(self.sim._h))
 
+    def set_smooth(self, smooth):
+        """el_mag_fld{ smooth_type = "stand" } with the given osiris_b200.smooth.Smooth; None = "none"."""
+        order = np.zeros(3, np.int32)
+        if smooth is None or not smooth.if_smooth():
+            check(self.sim._L.osgpu_emf_set_smooth(self.sim._h, ptr(order), 0, None))
+            return
+        sc = smooth.scoef if smooth.scoef is not None else smooth.setup(self.sim.dx, dtype=self.sim.dtype)
+        sc = np.ascontiguousarray(sc, self.sim.dtype)
+        order[:self.sim.dim] = smooth.order
+        check(self.sim._L.osgpu_emf_set_smooth(self.sim._h, ptr(order), int(smooth.max_order), ptr(sc)))
+
+    def update_particle_fld(self):
+        """update_particle_fld (emf/os-emf.f03:1065-1150): refresh e_part / b_part"""
+        check(self.sim._L.osgpu_emf_update_particle_fld(self.sim._h))
+
     def energy(self):
         out = np.zeros(6, np.float64)
         check(self.sim._L.osgpu_field_energy(self.sim._h, out.ctypes.data_as(C.POINTER(C.c_double))))
@@ -205,13 +220,16 @@ class Simulation:
     """The hot part of t_simulation (os-simulation.f03).  One instance per rank / GPU."""
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
-                 node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None):
+                 node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None,
+                 emf_smooth=None):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
         self.nx = [int(v) for v in nx]
         self.dx = [float(v) for v in dx]
         self.dt = float(dt)
+        if emf_smooth is not None:
+            smooth_order = max(smooth_order, emf_smooth.smooth_order())
         lo, up = min_gc(self.order, smooth_order)
         self.gc_emf = gc_emf if gc_emf is not None else ([lo] * dim, [up] * dim)
         self.gc_jay = gc_jay if gc_jay is not None else ([lo] * dim, [up] * dim)
@@ -243,6 +261,8 @@ class Simulation:
         self.nspecies = nspecies
         if smooth is not None:
             self.jay.set_smooth(smooth)
+        if emf_smooth is not None:
+            self.emf.set_smooth(emf_smooth)
 
     # padded host array shapes (numpy order: slowest first, component last)
     def _shape(self, gc):

@@ -7,7 +7,7 @@ from oracle.bindings import Oracle, aligned
 
 
 class OracleSim:
-    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None):
+    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None, emf_smooth=None):
         self.orc = Oracle(precision)
         self.dtype = self.orc.dtype
         self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
@@ -20,6 +20,8 @@ class OracleSim:
         self.j = np.zeros(sh(self.gc_jay), self.dtype)
         self.species = []
         self.smooth = smooth  # (order[dim], max_order, scoef[dim, 2 max_order + 1]) from Oracle.smooth_setup
+        self.emf_smooth = emf_smooth  # the same for el_mag_fld{ smooth_type = "stand" }
+        self.e_part, self.b_part = self.e, self.b
         # particles use dt rounded to their precision (spec/os-spec-vpush.f03:374)
         self.dtp = float(self.dtype(self.dt))
 
@@ -34,6 +36,16 @@ class OracleSim:
         self.orc.update_periodic(self.dim, self.e, self.nx, self.gc_emf, "replace")
         self.orc.update_periodic(self.dim, self.b, self.nx, self.gc_emf, "replace")
 
+    def emf_update_particle_fld(self):
+        """update_particle_fld (emf/os-emf.f03:1065-1150) with smooth_type "stand" """
+        if self.emf_smooth is None:
+            self.e_part, self.b_part = self.e, self.b
+            return
+        order, mo, sc = self.emf_smooth
+        self.e_part, self.b_part = self.e.copy(), self.b.copy()
+        self.orc.smooth(self.dim, self.e_part, self.nx, self.gc_emf, order, mo, sc)
+        self.orc.smooth(self.dim, self.b_part, self.nx, self.gc_emf, order, mo, sc)
+
     def advance_deposit(self):
         self.j[...] = 0
         ene = []
@@ -42,7 +54,7 @@ class OracleSim:
                 ene.append(0.0)
                 continue
             ene.append(self.orc.advance_deposit(self.dim, self.order, sp["ix"], sp["x"], sp["p"], sp["q"],
-                                                sp["rqm"], self.e, self.b, self.gc_emf, self.j, self.gc_jay,
+                                                sp["rqm"], self.e_part, self.b_part, self.gc_emf, self.j, self.gc_jay,
                                                 self.dx, self.dtp))
         return np.array(ene)
 
@@ -66,6 +78,7 @@ class OracleSim:
         ene = None
         for _ in range(nsteps):
             self.emf_update_boundary()
+            self.emf_update_particle_fld()
             ene = self.advance_deposit()
             self.particles_update_boundary()
             self.current_update_boundary()

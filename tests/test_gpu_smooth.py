@@ -118,3 +118,62 @@ def test_n_steps_with_smoothing_match_oracle(built, dim, prec):
     assert np.abs(b - ora.b).max() <= (1e-3 if prec == "f32" else 1e-9) * s
     assert sim.phase_times_ms()["current smooth"] > 0
     sim.close()
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("dim,types,orders", [(2, ["binomial", "binomial"], [1, 1]), (3, ["compensated"] * 3, [2, 2, 2]),
+                                              (3, ["binomial", "none", "tri6"], [2, 0, 0])])
+def test_field_smoothing_for_particles(built, dim, types, orders, prec):
+    """el_mag_fld{ smooth_type = "stand" }: the particles are pushed with smooth(e), smooth(b) while the
+    solver keeps e, b.  One push from identical inputs: x, p, ix bit-identical to the oracle (which pins
+    e_part / b_part bit for bit), then N full steps with field AND current smoothing."""
+    from osiris_b200.simulation import Simulation, min_gc
+    from osiris_b200.smooth import Smooth
+    from oracle.bindings import Oracle
+    interp = 2
+    nx = [37, 21] if dim == 2 else [19, 13, 11]
+    sm = Smooth(dim, type=types, order=orders)
+    lo, up = min_gc(interp, sm.smooth_order())
+    gc = ([lo] * dim, [up] * dim)
+    dt = 0.4 * min(DX[dim]) / np.sqrt(dim)
+    sim = Simulation(dim, interp, nx, DX[dim], dt, precision=prec, gc_emf=gc, gc_jay=gc, emf_smooth=sm, smooth=sm)
+    setup = Oracle(prec).smooth_setup(dim, types, orders)
+    ora = OracleSim(dim, interp, nx, DX[dim], dt, precision=prec, gc_emf=gc, gc_jay=gc, smooth=setup, emf_smooth=setup)
+    c = random_case(dim, interp, prec, nx, 4, seed=9, umax=0.2, efield=0.2, gc=gc)
+    ora.e[...] = c["e"]
+    ora.b[...] = c["b"]
+    sim.emf.upload(c["e"], c["b"])
+    n = c["q"].shape[0]
+    sp = sim.add_species("e", -1.0, 2 * n + 1024)
+    sp.upload(c["ix"], c["x"], c["u"], c["q"])
+    ora.add_species(-1.0, c["ix"], c["x"], c["u"], c["q"])
+    # one push, phase by phase
+    sim.emf.update_boundary(); ora.emf_update_boundary()
+    sim.emf.update_particle_fld(); ora.emf_update_particle_fld()
+    sim.part.advance_deposit(); ora.advance_deposit()
+    sim.part.update_boundary(); ora.particles_update_boundary()
+    d = sp.fill_data()
+    r = ora.species[0]
+    assert np.array_equal(d["ix"], r["ix"])
+    assert np.array_equal(d["x"], r["x"]) and np.array_equal(d["p"], r["p"])
+    e, b = sim.emf.fill_data()
+    assert np.array_equal(e, ora.e) and np.array_equal(b, ora.b)  # the solver's fields are not smoothed
+    sim.jay.update_boundary(); ora.current_update_boundary()
+    sim.jay.smooth(); ora.current_smooth()
+    sim.emf.advance(); ora.emf_advance()
+    # then whole steps
+    ene = sim.iter(5)
+    ene_r = ora.iter(5)
+    tol = 2e-4 if prec == "f32" else 1e-9
+    assert np.allclose(ene, ene_r, rtol=tol)
+    e, b = sim.emf.fill_data()
+    s = max(np.abs(ora.e).max(), np.abs(ora.b).max())
+    assert np.abs(e - ora.e).max() <= (1e-3 if prec == "f32" else 1e-9) * s
+    assert np.abs(b - ora.b).max() <= (1e-3 if prec == "f32" else 1e-9) * s
+    # switching it off returns to the unsmoothed fields
+    sim.emf.set_smooth(None)
+    ora.emf_smooth = None
+    ene = sim.iter(1)
+    ene_r = ora.iter(1)
+    assert np.allclose(ene, ene_r, rtol=tol)
+    sim.close()

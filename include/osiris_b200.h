@@ -63,8 +63,15 @@ typedef struct osgpu_config {
   int32_t smooth_order; /* current smoothing passes folded into gc (0 = none)            */
   int32_t no_tags;    /* 1: particles carry no tag (species{add_tag} off, the reference's default,
                        * spec/os-spec-define.f03:431); by-tag downloads are then unavailable      */
-  int32_t reserved[6];
+  /* species boundary condition at a physical wall (a side with no neighbour: non-periodic axis, rank
+   * on the edge), [lower/upper][axis]: spec/os-spec-boundary.f03:1293-1325.  A moving window makes the
+   * lower wall absorbing and the upper one specular on its axis (:306-318, :1276).  Field boundary
+   * conditions at such walls are NOT applied (that is what a moving window needs, p_bc_move_c;
+   * conducting / open walls are SURVEY.md 8f row 3). */
+  int32_t part_bc[2][OSGPU_MAX_DIM];
 } osgpu_config;
+#define OSGPU_PBC_ABSORB 0
+#define OSGPU_PBC_SPECULAR 1
 
 /* ---- library / topology helpers (no GPU needed) -------------------------------------- */
 const char *osgpu_version(void);
@@ -121,6 +128,19 @@ int osgpu_species_download(osgpu_sim *sim, int sp_id, int32_t *ix, void *x, void
  * other: the download of one overlaps the upload of the next. */
 int osgpu_species_download_async(osgpu_sim *sim, int sp_id, int32_t *ix, void *x, void *p, void *q,
                                  int64_t *tag);
+
+/* ---- moving window ------------------------------------------------ */
+/* One call = emf%move_window + part%move_window of iter_sim (os-simulation.f03:529-548) for
+ * nmove[dim] = nx_move(g_space) cells (the host keeps t_space and decides when the window moves):
+ * E, B slide down and are zero-filled (vdf/os-vdf.f03:56-205), every particle's ix drops by nmove
+ * (spec/os-species.f03:171-229) and leavers meet migration / part_bc.  Call it before
+ * osgpu_step; follow it with osgpu_species_inject for the plasma the window uncovered. */
+int osgpu_move_window(osgpu_sim *sim, const int32_t *nmove);
+/* np new particles (host arrays in the reference layout, ix local to this rank, inside 1..nx) join
+ * the species: the inject() of move_window_species (spec/os-species.f03:218-226) with the particles
+ * created by the host's psource.  tag may be NULL. */
+int osgpu_species_inject(osgpu_sim *sim, int sp_id, int64_t np, const int32_t *ix, const void *x,
+                         const void *p, const void *q, const int64_t *tag);
 
 /* ---- fields: t_emf%e, t_emf%b, t_current%pf(1) ------------------------------------------ */
 int osgpu_fields_upload(osgpu_sim *sim, const void *e, const void *b);

@@ -73,6 +73,11 @@ class Oracle:
         L.oracle_field_energy.restype = None
         L.oracle_deposit_rho.argtypes = [C.c_int, C.c_int, _i32p, rp, rp, C.c_long, _f64p, _i32p, _i32p]
         L.oracle_deposit_rho.restype = None
+        L.oracle_move_window_vdf.argtypes = [C.c_int, rp, C.c_int, _i32p, _i32p, _i32p, _i32p]
+        L.oracle_move_window_vdf.restype = None
+        L.oracle_particles_bc.argtypes = [C.c_int, _i32p, rp, rp, C.c_long, _i32p, _i32p,
+                                          np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")]
+        L.oracle_particles_bc.restype = None
         L.oracle_smooth_setup.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _i32p, _i32p, rp]
         L.oracle_smooth_setup.restype = None
         L.oracle_smooth.argtypes = [C.c_int, rp, _i32p, _i32p, _i32p, _i32p, C.c_int, rp]
@@ -147,6 +152,24 @@ class Oracle:
         self.lib.oracle_deposit_rho(dim, order, ix, x, q, q.shape[0], rho, size, self._i(gc[0]))
         return rho
 
+
+    def move_window_vdf(self, dim, f, nx, gc, nmove):
+        nm = np.zeros(3, np.int32)
+        nm[:dim] = nmove
+        self.lib.oracle_move_window_vdf(dim, f, f.shape[-1], self._i(nx), self._i(gc[0]), self._i(gc[1]), nm)
+
+    PART_BC = {"periodic": 1, "absorbing": 2, "specular": 3}
+
+    def particles_bc(self, dim, ix, x, p, nx, bc):
+        """bc = ([lower per axis], [upper per axis]) of 'periodic' | 'absorbing' | 'specular'; in place on
+        ix, x, p; returns the keep mask."""
+        code = np.zeros(6, np.int32)
+        for sd in range(2):
+            for d in range(dim):
+                code[sd * 3 + d] = self.PART_BC[bc[sd][d]]
+        keep = np.ones(ix.shape[0], np.uint8)
+        self.lib.oracle_particles_bc(dim, ix, x, p, ix.shape[0], self._i(nx), code, keep)
+        return keep.astype(bool)
 
     SMOOTH_TYPES = {"none": 0, "custom": 1, "binomial": 2, "compensated": 3, "5pass": 4, "tri6": 5,
                     "tri8": 6, "digital": 11}

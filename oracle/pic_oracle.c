@@ -1014,3 +1014,55 @@ void oracle_smooth(int dim, REAL *f, const int *nx, const int *gcl, const int *g
       }
   }
 }
+
+/* ------------------------------------------------------------------------------------
+ * Moving window.
+ * move_window_vdf (vdf/os-vdf.f03:56-205): along every axis with nmove > 0 the data slide down,
+ * f(i) = f(i + nmove) for i = lbound .. ubound - nmove, and the uncovered cells are set to 0.
+ * f: (fdim, S1, S2[, S3]) with S = nx + gcl + gcu.
+ * ---------------------------------------------------------------------------------- */
+void oracle_move_window_vdf(int dim, REAL *f, int fdim, const int *nx, const int *gcl, const int *gcu,
+                            const int *nmove) {
+  long S[3] = {1, 1, 1}, st[3];
+  for (int d = 0; d < dim; d++) S[d] = nx[d] + gcl[d] + gcu[d];
+  st[0] = fdim; st[1] = st[0] * S[0]; st[2] = st[1] * S[1];
+  for (int ax = 0; ax < dim; ax++) {
+    const int n = nmove[ax];
+    if (n <= 0) continue;
+    const int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+    for (long j2 = 0; j2 < S[a2]; j2++)
+      for (long j1 = 0; j1 < S[a1]; j1++) {
+        REAL *line = f + j1 * st[a1] + j2 * st[a2];
+        for (long i = 0; i < S[ax]; i++)
+          for (int c = 0; c < fdim; c++)
+            line[i * st[ax] + c] = (i + n < S[ax]) ? line[(i + n) * st[ax] + c] : R(0.0);
+      }
+  }
+}
+
+/* Species boundaries of a single rank, axis by axis, lower side then upper side
+ * (update_boundary_species -> process_phys_boundary, spec/os-spec-boundary.f03:1099-1232, 1238-1325).
+ * bc[side*3 + axis]: 1 periodic (ix -+ nx, :1280-1290), 2 absorbing (particle removed, :1293-1300),
+ * 3 specular (p_d -> -p_d, ix -> 1 | nx, x -> -x, :1302-1325; the upper wall of a moving window,
+ * :1276).  keep[k] = 0 marks a removed particle. */
+void oracle_particles_bc(int dim, int *ix, REAL *x, REAL *p, long np, const int *nx, const int *bc,
+                         unsigned char *keep) {
+  for (long k = 0; k < np; k++) keep[k] = 1;
+  for (int d = 0; d < dim; d++)
+    for (long k = 0; k < np; k++) {
+      if (!keep[k]) continue;
+      int *i = &ix[dim * k + d];
+      const int side = (*i < 1) ? 0 : (*i > nx[d] ? 1 : -1);
+      if (side < 0) continue;
+      switch (bc[side * 3 + d]) {
+      case 1: *i += side ? -nx[d] : nx[d]; break;
+      case 2: keep[k] = 0; break;
+      case 3:
+        p[3 * k + d] = -p[3 * k + d];
+        *i = side ? nx[d] : 1;
+        x[dim * k + d] = -x[dim * k + d];
+        break;
+      default: break;
+      }
+    }
+}

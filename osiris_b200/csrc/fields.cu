@@ -174,6 +174,38 @@ template int smooth_field<double>(const Grid &, Field3<double>, Field3<double>, 
                                   const SmoothCoef<double> *, cudaStream_t, long long *);
 
 // ---------------------------------------------------------------------------------------------
+// Moving window: f(i) = f(i + nmove) over the t_vdf's own bounds, the cells uncovered at the upper end
+// set to zero (move_window_vdf, source/vdf/os-vdf.f03:56-205).  Out of place (src -> dst); points of
+// the storage outside the box are copied.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+    shift_kernel(Field3<T> dst, Field3<const T> src, Grid g, SmoothBox bx, int n0, int n1, int n2) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= g.S[0]) return;
+  const int i1 = blockIdx.y, i2 = blockIdx.z;
+  const long long p = g.at(i0, i1, i2);
+  const bool in = i0 >= bx.lo[0] && i0 <= bx.hi[0] && i1 >= bx.lo[1] && i1 <= bx.hi[1] && i2 >= bx.lo[2] && i2 <= bx.hi[2];
+  const bool have = (i0 + n0 <= bx.hi[0]) && (i1 + n1 <= bx.hi[1]) && (i2 + n2 <= bx.hi[2]);
+  const long long q = g.at(i0 + n0, i1 + n1, i2 + n2);
+#pragma unroll
+  for (int c = 0; c < 3; c++) dst.c[c][p] = in ? (have ? src.c[c][q] : T(0)) : src.c[c][p];
+}
+template <typename T>
+int shift_field(const Grid &g, Field3<T> f, Field3<T> tmp, const SmoothBox &bx, const int *nmove, cudaStream_t st,
+                long long *launches) {
+  const dim3 blk(128), grid((g.S[0] + 127) / 128, g.S[1], g.S[2]);
+  Field3<const T> cf{{f.c[0], f.c[1], f.c[2]}};
+  shift_kernel<T><<<grid, blk, 0, st>>>(tmp, cf, g, bx, nmove[0], g.dim > 1 ? nmove[1] : 0, g.dim > 2 ? nmove[2] : 0);
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  OSGPU_CUDA(cudaMemcpyAsync(f.c[0], tmp.c[0], sizeof(T) * 3 * g.vol, cudaMemcpyDeviceToDevice, st));
+  return OSGPU_OK;
+}
+template int shift_field<float>(const Grid &, Field3<float>, Field3<float>, const SmoothBox &, const int *, cudaStream_t, long long *);
+template int shift_field<double>(const Grid &, Field3<double>, Field3<double>, const SmoothBox &, const int *, cudaStream_t, long long *);
+
+// ---------------------------------------------------------------------------------------------
 // Slab helpers.  A slab is the padded range [a0, a1] along `axis` times the full padded extent of
 // the other axes (that is how update_boundary_vdf propagates edges and corners, os-vdf-comm.f90
 // :686-719).  r enumerates the slab with the x index fastest.

@@ -33,6 +33,10 @@ struct SmoothBox {
 template <typename T>
 int smooth_field(const Grid &g, Field3<T> src, Field3<T> dst, Field3<T> tmp, const SmoothBox &bx, const int *order,
                  const SmoothCoef<T> *coef, cudaStream_t st, long long *launches);
+// moving window: f(i) = f(i + nmove) inside the box, zero where uncovered; tmp = three scratch planes
+template <typename T>
+int shift_field(const Grid &g, Field3<T> f, Field3<T> tmp, const SmoothBox &bx, const int *nmove, cudaStream_t st,
+                long long *launches);
 template <typename T>
 int field_energy(const Grid &g, T *const *comps6, double *dev_out6, cudaStream_t st, long long *launches);
 

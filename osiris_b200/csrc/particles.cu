@@ -43,16 +43,20 @@ __device__ __forceinline__ int tile_cell_index(int cell, const Tiling &tl) {
 // every tile sorted by cell with its cell offsets known, so the first push after an upload already
 // runs the per-cell register accumulation (an unsorted tile sends every particle through the
 // piece lists).  Pass 1: particles per cell.
+// `shift`: cells subtracted from ix first (moving window, move_window_species spec/os-species.f03:171-229).
+// A particle outside 1..nx is an error on upload; with `to_movers` (window shift) it is handed to the
+// mover buffer with its shifted ix and meets the boundary conditions / migration there.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    count_kernel(AosParticles<T> in, long long np, int dim, Tiling tl, Grid g, int *cell_cnt, int *errflag) {
+    count_kernel(AosParticles<T> in, long long np, int dim, Tiling tl, Grid g, Shift3 shift, int to_movers,
+                 int *cell_cnt, int *errflag) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np;
        i += (long long)gridDim.x * blockDim.x) {
     int ix[3] = {1, 1, 1};
-    for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d];
+    for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d] - shift.n[d];
     int t, c;
     if (locate(ix, dim, tl, g.nx, &t, &c)) atomicAdd(&cell_cnt[(size_t)t * TILE_NCELL + tile_cell_index(c, tl)], 1);
-    else atomicOr(errflag, ERRF_BAD_CELL);
+    else if (!to_movers) atomicOr(errflag, ERRF_BAD_CELL);
   }
 }
 
@@ -90,14 +94,25 @@ __global__ void __launch_bounds__(TILE_NCELL)
 // Pass 3: every particle to tile_off[tile] + cell_start[tile][cell] + (its turn inside the cell)
 template <typename T>
 __global__ void __launch_bounds__(256)
-    scatter_kernel(AosParticles<T> in, long long np, long long tag_base, int dim, Tiling tl, Grid g,
-                   const int *tile_off, const int *cell_start, int *cursor, SpeciesView<T> sp) {
+    scatter_kernel(AosParticles<T> in, long long np, long long tag_base, int dim, Tiling tl, Grid g, Shift3 shift,
+                   int to_movers, MoverView<T> mv, int *errflag, const int *tile_off, const int *cell_start,
+                   int *cursor, SpeciesView<T> sp) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np;
        i += (long long)gridDim.x * blockDim.x) {
     int ix[3] = {1, 1, 1};
-    for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d];
+    for (int d = 0; d < dim; d++) ix[d] = in.ix[dim * i + d] - shift.n[d];
     int t, c;
-    if (!locate(ix, dim, tl, g.nx, &t, &c)) continue;
+    if (!locate(ix, dim, tl, g.nx, &t, &c)) {
+      if (to_movers) {
+        const int m = atomicAdd(mv.count, 1);
+        if (m >= mv.cap) { atomicOr(errflag, ERRF_MOVER_OVERFLOW); continue; }
+        for (int d = 0; d < dim; d++) { mv.x[d][m] = in.x[dim * i + d]; mv.ix[d][m] = ix[d]; }
+        for (int d = 0; d < 3; d++) mv.p[d][m] = in.p[3 * i + d];
+        mv.q[m] = in.q[i];
+        if (mv.tag) mv.tag[m] = in.tag ? in.tag[i] : tag_base + i;
+      }
+      continue;
+    }
     const int lc = tile_cell_index(c, tl);
     const long long s = (long long)tile_off[t] + cell_start[(size_t)t * (TILE_NCELL + 1) + lc] +
                         atomicAdd(&cursor[(size_t)t * TILE_NCELL + lc], 1);
@@ -152,29 +167,59 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// Movers: wrap the axes on which this rank is its own periodic neighbour
-// (spec/os-spec-boundary.f03:1280-1290), then count arrivals per destination tile.
+// Movers meet the boundaries of this rank, axis by axis, lower then upper side
+// (update_boundary_species -> process_phys_boundary, spec/os-spec-boundary.f03:1238-1465):
+//   PBC_WRAP     this rank is its own periodic neighbour: ix +- nx (:1280-1290)
+//   PBC_ABSORB   physical wall, particle removed (:1293-1300; the lower wall of a moving window)
+//   PBC_SPECULAR physical wall, p_d -> -p_d, ix -> 1 | nx, x -> -x (:1302-1325; the upper wall of a
+//                moving window behaves like this, :1276)
+//   PBC_NONE     another rank's side: the particle was migrated before, out of range here is an error
+// then the arrivals per destination tile are counted.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    route_kernel(MoverView<T> mv, int dim, Tiling tl, Grid g, int wrap0, int wrap1, int wrap2, int *tile_arr,
-                 int *errflag) {
+    route_kernel(MoverView<T> mv, int dim, Tiling tl, Grid g, PartBc bc, int *tile_arr, int *errflag) {
   const int n = min(*mv.count, mv.cap);
-  const int wrap[3] = {wrap0, wrap1, wrap2};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int ix[3] = {1, 1, 1};
     if (mv.ix[0][i] == INT_MIN) continue;  // sent to another rank
-    for (int d = 0; d < dim; d++) {
+    bool gone = false;
+    for (int d = 0; d < dim && !gone; d++) {
       int v = mv.ix[d][i];
-      if (wrap[d]) {
-        if (v < 1) v += g.nx[d];
-        else if (v > g.nx[d]) v -= g.nx[d];
+      const int side = (v < 1) ? 0 : (v > g.nx[d] ? 1 : -1);
+      if (side >= 0) {
+        const int type = bc.t[side][d];
+        if (type == PBC_WRAP) {
+          v += side ? -g.nx[d] : g.nx[d];
+        } else if (type == PBC_ABSORB) {
+          gone = true;
+        } else if (type == PBC_SPECULAR) {
+          mv.p[d][i] = -mv.p[d][i];
+          mv.x[d][i] = -mv.x[d][i];
+          v = side ? g.nx[d] : 1;
+        }
         mv.ix[d][i] = v;
       }
       ix[d] = v;
     }
+    if (gone) { mv.ix[0][i] = INT_MIN; continue; }
     int t, c;
     if (locate(ix, dim, tl, g.nx, &t, &c)) atomicAdd(&tile_arr[t], 1);
     else atomicOr(errflag, ERRF_BAD_CELL);
+  }
+}
+
+// host-layout particles appended to the mover buffer (injection, e.g. the plasma a moving window
+// uncovers: inject -> create particles, spec/os-species.f03:218-226)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    inject_kernel(AosParticles<T> in, int np, long long tag_base, int dim, MoverView<T> mv, int base) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) {
+    const int m = base + i;
+    for (int d = 0; d < dim; d++) { mv.x[d][m] = in.x[dim * i + d]; mv.ix[d][m] = in.ix[dim * i + d]; }
+    for (int d = 0; d < 3; d++) mv.p[d][m] = in.p[3 * i + d];
+    mv.q[m] = in.q[i];
+    if (mv.tag) mv.tag[m] = in.tag ? in.tag[i] : tag_base + i;
+    if (i == 0) *mv.count = base + np;
   }
 }
 
@@ -305,18 +350,20 @@ static int blocks_for(long long n) {
 }
 
 template <typename T>
-int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *cell_cnt,
-              int *cell_start, int *tile_cnt, int *tile_nsorted, int *errflag, cudaStream_t st, long long *launches) {
-  if (np > 0) count_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, g.dim, tl, g, cell_cnt, errflag);
+int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, const Shift3 &shift,
+              int to_movers, int *cell_cnt, int *cell_start, int *tile_cnt, int *tile_nsorted, int *errflag,
+              cudaStream_t st, long long *launches) {
+  if (np > 0) count_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, g.dim, tl, g, shift, to_movers, cell_cnt, errflag);
   cell_scan_kernel<<<tl.ntile, TILE_NCELL, 0, st>>>(cell_cnt, cell_start, tile_cnt, tile_nsorted);
   LAUNCHED(2);
 }
 template <typename T>
 int bin_scatter(const AosParticles<T> &in, long long np, long long tag_base, const Grid &g, const Tiling &tl,
-                const int *tile_off, const int *cell_start, int *cursor, const SpeciesView<T> &sp, cudaStream_t st,
-                long long *launches) {
+                const Shift3 &shift, int to_movers, const MoverView<T> &mv, int *errflag, const int *tile_off,
+                const int *cell_start, int *cursor, const SpeciesView<T> &sp, cudaStream_t st, long long *launches) {
   if (np == 0) return OSGPU_OK;
-  scatter_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, tag_base, g.dim, tl, g, tile_off, cell_start, cursor, sp);
+  scatter_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, tag_base, g.dim, tl, g, shift, to_movers, mv, errflag,
+                                                    tile_off, cell_start, cursor, sp);
   LAUNCHED(1);
 }
 template <typename T>
@@ -334,10 +381,17 @@ int movers_download(const MoverView<T> &mv, long long out_base, const Grid &g, i
   LAUNCHED(1);
 }
 template <typename T>
-int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *wrap, const int *tile_off,
+int movers_inject(const AosParticles<T> &in, int np, long long tag_base, const Grid &g, const MoverView<T> &mv,
+                  int base, cudaStream_t st, long long *launches) {
+  if (np == 0) return OSGPU_OK;
+  inject_kernel<T><<<blocks_for(np), 256, 0, st>>>(in, np, tag_base, g.dim, mv, base);
+  LAUNCHED(1);
+}
+template <typename T>
+int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const PartBc &bc, const int *tile_off,
                  const int *tile_cnt, int *tile_arr, int *errflag, cudaStream_t st, long long *launches) {
   OSGPU_CUDA(cudaMemsetAsync(tile_arr, 0, sizeof(int) * tl.ntile, st));
-  route_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, tl, g, wrap[0], wrap[1], wrap[2], tile_arr, errflag);
+  route_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, tl, g, bc, tile_arr, errflag);
   capacity_kernel<<<(tl.ntile + 255) / 256, 256, 0, st>>>(tile_off, tile_cnt, tile_arr, tl.ntile, errflag);
   LAUNCHED(2);
 }
@@ -370,16 +424,19 @@ int movers_unpack(const uint32_t *buf, int nrec, const Grid &g, int axis, int ad
 }
 
 #define INST(T)                                                                                               \
-  template int bin_count<T>(const AosParticles<T> &, long long, const Grid &, const Tiling &, int *, int *, int *, int *, int *,    \
-                            cudaStream_t, long long *);                                                       \
+  template int bin_count<T>(const AosParticles<T> &, long long, const Grid &, const Tiling &, const Shift3 &, \
+                            int, int *, int *, int *, int *, int *, cudaStream_t, long long *);               \
   template int bin_scatter<T>(const AosParticles<T> &, long long, long long, const Grid &, const Tiling &,     \
-                              const int *, const int *, int *, const SpeciesView<T> &, cudaStream_t, long long *); \
+                              const Shift3 &, int, const MoverView<T> &, int *, const int *, const int *,     \
+                              int *, const SpeciesView<T> &, cudaStream_t, long long *);                      \
+  template int movers_inject<T>(const AosParticles<T> &, int, long long, const Grid &, const MoverView<T> &,   \
+                                int, cudaStream_t, long long *);                                              \
   template int gather_download<T>(const SpeciesView<T> &, const int *, const int *, const long long *,         \
                                   const Grid &, const Tiling &, int *, T *, T *, T *, long long *, int,        \
                                   cudaStream_t, long long *);                                                 \
   template int movers_download<T>(const MoverView<T> &, long long, const Grid &, int *, T *, T *, T *,         \
                                   long long *, int, cudaStream_t, long long *);                               \
-  template int movers_route<T>(const MoverView<T> &, const Grid &, const Tiling &, const int *, const int *,   \
+  template int movers_route<T>(const MoverView<T> &, const Grid &, const Tiling &, const PartBc &, const int *, \
                                const int *, int *, int *, cudaStream_t, long long *);                         \
   template int movers_insert<T>(const MoverView<T> &, const Grid &, const Tiling &, const int *, int *,        \
                                 const SpeciesView<T> &, cudaStream_t, long long *);                           \

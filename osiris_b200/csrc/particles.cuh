@@ -15,15 +15,30 @@ template <typename T> struct AosParticles {
   const long long *tag;  // may be null
 };
 
+// cells subtracted from ix before binning (moving window)
+struct Shift3 {
+  int n[3];
+};
+// what a mover meets on each side [lower/upper][axis] of this rank (route_kernel)
+enum : int { PBC_NONE = 0, PBC_WRAP = 1, PBC_ABSORB = 2, PBC_SPECULAR = 3 };
+struct PartBc {
+  int t[2][3];
+};
+
 // upload = counting sort by (tile, cell).  cell_cnt: [ntile][TILE_NCELL] zeroed scratch (counts, then
 // scatter cursors); cell_start: [ntile][TILE_NCELL + 1] offsets; tile_cnt / tile_nsorted: per tile
 template <typename T>
-int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, int *cell_cnt,
-              int *cell_start, int *tile_cnt, int *tile_nsorted, int *errflag, cudaStream_t st, long long *launches);
+int bin_count(const AosParticles<T> &in, long long np, const Grid &g, const Tiling &tl, const Shift3 &shift,
+              int to_movers, int *cell_cnt, int *cell_start, int *tile_cnt, int *tile_nsorted, int *errflag,
+              cudaStream_t st, long long *launches);
 template <typename T>
 int bin_scatter(const AosParticles<T> &in, long long np, long long tag_base, const Grid &g, const Tiling &tl,
-                const int *tile_off, const int *cell_start, int *cursor, const SpeciesView<T> &sp, cudaStream_t st,
-                long long *launches);
+                const Shift3 &shift, int to_movers, const MoverView<T> &mv, int *errflag, const int *tile_off,
+                const int *cell_start, int *cursor, const SpeciesView<T> &sp, cudaStream_t st, long long *launches);
+// np host-layout particles appended to the mover buffer at `base` (count becomes base + np)
+template <typename T>
+int movers_inject(const AosParticles<T> &in, int np, long long tag_base, const Grid &g, const MoverView<T> &mv,
+                  int base, cudaStream_t st, long long *launches);
 template <typename T>
 int gather_download(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const long long *out_off,
                     const Grid &g, const Tiling &tl, int *oix, T *ox, T *op, T *oq, long long *otag, int by_tag,
@@ -32,7 +47,7 @@ template <typename T>
 int movers_download(const MoverView<T> &mv, long long out_base, const Grid &g, int *oix, T *ox, T *op, T *oq,
                     long long *otag, int by_tag, cudaStream_t st, long long *launches);
 template <typename T>
-int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *wrap, const int *tile_off,
+int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const PartBc &bc, const int *tile_off,
                  const int *tile_cnt, int *tile_arr, int *errflag, cudaStream_t st, long long *launches);
 template <typename T>
 int movers_insert(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *tile_off, int *tile_cnt,

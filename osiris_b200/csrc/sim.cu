@@ -60,6 +60,9 @@ struct SimBase {
   virtual int species_update_boundary(int id) = 0;
   virtual int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) = 0;
   virtual int sync_all() = 0;
+  virtual int move_window(const int *nmove) = 0;
+  virtual int species_inject(int id, long long np, const int *ix, const void *x, const void *p, const void *q,
+                             const long long *tag) = 0;
   virtual int current_set_smooth(const int *order, int max_order, const void *scoef) = 0;
   virtual int emf_set_smooth(const int *order, int max_order, const void *scoef) = 0;
   virtual int emf_update_particle_fld() = 0;
@@ -515,6 +518,26 @@ template <typename T> struct Sim final : SimBase {
     return OSGPU_OK;
   }
 
+  // counting sort by (tile, cell) of np host-layout particles staged on the device into the species'
+  // buffer: count, per-tile scan (cell offsets, tile counts), layout on the host, scatter.  With
+  // to_movers (window shift) particles whose shifted cell lies outside 1..nx go to the mover buffer.
+  int sort_from_staging(Species &s, const AosParticles<T> &in, long long np, const Shift3 &shift, bool to_movers) {
+    OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
+    s.movers_pending = false;
+    if (!s.cell_cur) OSGPU_CUDA(cudaMalloc(&s.cell_cur, sizeof(int) * (size_t)tl.ntile * pic::TILE_NCELL));
+    OSGPU_CUDA(cudaMemsetAsync(s.cell_cur, 0, sizeof(int) * (size_t)tl.ntile * pic::TILE_NCELL, st));
+    OSGPU_TRY(bin_count<T>(in, np, g, tl, shift, to_movers, s.cell_cur, s.cell_start, s.tile_cnt, s.tile_nsorted, d_err, st, &launches));
+    std::vector<int> cnt(tl.ntile), off;
+    OSGPU_TRY(ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile));
+    OSGPU_TRY(check_err("species_upload"));  // synchronises: cnt is valid
+    OSGPU_TRY(layout_offsets(cnt, s.cap, &off, &s.max_range));
+    s.cur = 0;
+    OSGPU_TRY(ctl_write(s.tile_off[0], off.data(), sizeof(int) * (tl.ntile + 1)));
+    OSGPU_TRY(bin_scatter<T>(in, np, 0, g, tl, shift, to_movers, s.mv, d_err, s.tile_off[0], s.cell_start, s.cell_cur, s.v[0], st, &launches));
+    if (to_movers) s.movers_pending = true;
+    return OSGPU_OK;
+  }
+
   int species_upload_end(int id) override {
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
@@ -525,28 +548,9 @@ template <typename T> struct Sim final : SimBase {
     s.up_slot = -1;
     up_owner[slot] = -1;
     int rc = OSGPU_OK;
-    do {
-      if (cudaStreamWaitEvent(st, ev_up_done[slot], 0) != cudaSuccess) { rc = OSGPU_ERR_CUDA; break; }
-      cudaMemsetAsync(s.mv.count, 0, sizeof(int), st);
-      s.movers_pending = false;
-      // counting sort by (tile, cell): count, per-tile scan (cell offsets, tile counts), scatter
-      if (!s.cell_cur) {
-        if (cudaMalloc(&s.cell_cur, sizeof(int) * (size_t)tl.ntile * pic::TILE_NCELL) != cudaSuccess) {
-          set_error("cell cursor allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-          rc = OSGPU_ERR_CUDA;
-          break;
-        }
-      }
-      cudaMemsetAsync(s.cell_cur, 0, sizeof(int) * (size_t)tl.ntile * pic::TILE_NCELL, st);
-      if ((rc = bin_count<T>(in, np, g, tl, s.cell_cur, s.cell_start, s.tile_cnt, s.tile_nsorted, d_err, st, &launches)) != OSGPU_OK) break;
-      std::vector<int> cnt(tl.ntile), off;
-      if ((rc = ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile)) != OSGPU_OK) break;
-      if ((rc = check_err("species_upload")) != OSGPU_OK) break;  // synchronises: cnt is valid
-      if ((rc = layout_offsets(cnt, s.cap, &off, &s.max_range)) != OSGPU_OK) break;
-      s.cur = 0;
-      if ((rc = ctl_write(s.tile_off[0], off.data(), sizeof(int) * (tl.ntile + 1))) != OSGPU_OK) break;
-      if ((rc = bin_scatter<T>(in, np, 0, g, tl, s.tile_off[0], s.cell_start, s.cell_cur, s.v[0], st, &launches)) != OSGPU_OK) break;
-    } while (0);
+    if (cudaStreamWaitEvent(st, ev_up_done[slot], 0) != cudaSuccess) rc = OSGPU_ERR_CUDA;
+    const Shift3 none{{0, 0, 0}};
+    if (rc == OSGPU_OK) rc = sort_from_staging(s, in, np, none, false);
     cudaEventRecord(ev_up_free[slot], st);  // the staging area may be overwritten after this point
     return rc;
   }
@@ -618,6 +622,103 @@ template <typename T> struct Sim final : SimBase {
       }
     } while (0);
     return rc;
+  }
+
+  // Moving window (os-simulation.f03:529-548): E and B slide down by nmove cells, zero where
+  // uncovered (emf%move_window -> move_window_vdf, vdf/os-vdf.f03:56-205); every particle's cell
+  // index drops by nmove (move_window_species, spec/os-species.f03:171-229) and the particles that
+  // leave the rank's box meet the boundary conditions / migration like any other leaver.  The tiles
+  // are rebuilt by one counting sort of the whole species (a tile-local shift would re-bin one cell
+  // column of every tile anyway).  J is recomputed from scratch each step and does not move.
+  int move_window(const int *nmove) override {
+    int nm[3] = {0, 0, 0};
+    bool any = false;
+    for (int d = 0; d < dim; d++) {
+      nm[d] = nmove[d];
+      if (nm[d] < 0) { set_error("Illegal move, only positive moves allowed"); return OSGPU_ERR_INVALID; }
+      if (nm[d] > cfg.gc_emf[0][d] || nm[d] > cfg.gc_emf[1][d]) { set_error("Illegal move, too many cells along direction %d", d + 1); return OSGPU_ERR_INVALID; }
+      any |= nm[d] > 0;
+    }
+    if (!any) return OSGPU_OK;
+    if (!jtmp) OSGPU_CUDA(cudaMalloc(&jtmp, sizeof(T) * 3 * g.vol));
+    SmoothBox bx;
+    for (int d = 0; d < 3; d++) {
+      bx.lo[d] = (d < dim) ? g.gl[d] - cfg.gc_emf[0][d] : 0;
+      bx.hi[d] = (d < dim) ? g.gl[d] + g.nx[d] + cfg.gc_emf[1][d] - 1 : 0;
+    }
+    Field3<T> tmp{{jtmp, jtmp + g.vol, jtmp + 2 * g.vol}};
+    OSGPU_TRY(shift_field<T>(g, B, tmp, bx, nm, st, &launches));
+    OSGPU_TRY(shift_field<T>(g, E, tmp, bx, nm, st, &launches));
+    const Shift3 sh{{nm[0], nm[1], nm[2]}};
+    for (size_t i = 0; i < sp.size(); i++) {
+      Species &s = sp[i];
+      if (!s.created) continue;
+      if (s.movers_pending) { set_error("move_window: species %d has unprocessed leavers", (int)i); return OSGPU_ERR_INVALID; }
+      std::vector<int> cnt(tl.ntile);
+      OSGPU_TRY(ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile));
+      OSGPU_TRY(ctl_sync());
+      std::vector<long long> ooff(tl.ntile + 1);
+      long long np = 0;
+      for (int t = 0; t < tl.ntile; t++) { ooff[t] = np; np += cnt[t]; }
+      if (np == 0) continue;
+      const size_t bix = sizeof(int) * dim * np, bx_ = sizeof(T) * dim * np, bp = sizeof(T) * 3 * np, bq = sizeof(T) * np;
+      const size_t btag = cfg.no_tags ? 0 : sizeof(long long) * np, boff = sizeof(long long) * (tl.ntile + 1);
+      const size_t al = 256;
+      auto up = [&](size_t v) { return (v + al - 1) / al * al; };
+      char *stage = nullptr;
+      OSGPU_TRY(stage_get(up(bix) + up(bx_) + up(bp) + up(bq) + up(btag) + up(boff) + al, &stage));
+      char *c = stage;
+      int *oix = (int *)c; c += up(bix);
+      T *ox = (T *)c; c += up(bx_);
+      T *op = (T *)c; c += up(bp);
+      T *oq = (T *)c; c += up(bq);
+      long long *otag = cfg.no_tags ? nullptr : (long long *)c; c += up(btag);
+      long long *doff = (long long *)c;
+      OSGPU_TRY(ctl_write(doff, ooff.data(), boff));
+      OSGPU_TRY(gather_download<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, doff, g, tl, oix, ox, op, oq, otag, 0, st, &launches));
+      AosParticles<T> in{oix, ox, op, oq, otag};
+      OSGPU_TRY(sort_from_staging(s, in, np, sh, true));
+      OSGPU_TRY(species_update_boundary((int)i));
+    }
+    return OSGPU_OK;
+  }
+
+  // New particles from host arrays (Fortran layout, ix local to this rank) join a species: they enter
+  // through the mover buffer and are inserted like arrivals (unsorted tail of their tiles).  This is
+  // where the plasma a moving window uncovers comes in (inject, spec/os-species.f03:218-226; the host's
+  // psource creates the particles).
+  int species_inject(int id, long long np, const int *ix, const void *x, const void *p, const void *q,
+                     const long long *tag) override {
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    Species &s = sp[id];
+    if (np <= 0) return OSGPU_OK;
+    if (s.movers_pending) { set_error("inject: species %d has unprocessed leavers", id); return OSGPU_ERR_INVALID; }
+    if (np > s.mv.cap) { set_error("inject: %lld particles exceed the mover buffer (%d)", np, s.mv.cap); return OSGPU_ERR_CAPACITY; }
+    const size_t bix = sizeof(int) * dim * np, bx_ = sizeof(T) * dim * np, bp = sizeof(T) * 3 * np, bq = sizeof(T) * np;
+    const size_t btag = tag ? sizeof(long long) * np : 0;
+    const size_t al = 256;
+    auto up = [&](size_t v) { return (v + al - 1) / al * al; };
+    char *stage = nullptr;
+    OSGPU_TRY(stage_get(up(bix) + up(bx_) + up(bp) + up(bq) + up(btag) + al, &stage));
+    char *c = stage;
+    AosParticles<T> in;
+    in.ix = (const int *)c; c += up(bix);
+    in.x = (const T *)c; c += up(bx_);
+    in.p = (const T *)c; c += up(bp);
+    in.q = (const T *)c; c += up(bq);
+    in.tag = tag ? (const long long *)c : nullptr;
+    OSGPU_CUDA(cudaMemcpyAsync((void *)in.ix, ix, bix, cudaMemcpyHostToDevice, st));
+    OSGPU_CUDA(cudaMemcpyAsync((void *)in.x, x, bx_, cudaMemcpyHostToDevice, st));
+    OSGPU_CUDA(cudaMemcpyAsync((void *)in.p, p, bp, cudaMemcpyHostToDevice, st));
+    OSGPU_CUDA(cudaMemcpyAsync((void *)in.q, q, bq, cudaMemcpyHostToDevice, st));
+    if (tag) OSGPU_CUDA(cudaMemcpyAsync((void *)in.tag, tag, btag, cudaMemcpyHostToDevice, st));
+    const long long have = species_count(id);
+    if (have < 0) return OSGPU_ERR_CUDA;
+    OSGPU_TRY(movers_inject<T>(in, (int)np, have, g, s.mv, 0, st, &launches));
+    s.movers_pending = true;
+    OSGPU_TRY(species_update_boundary(id));
+    OSGPU_CUDA(cudaStreamSynchronize(st));  // the host arrays and the staging area are free again
+    return OSGPU_OK;
   }
 
   // fill_data without the wait: the gather runs on the handle's stream, the device -> host copies on
@@ -906,14 +1007,27 @@ template <typename T> struct Sim final : SimBase {
   }
 
   // migrate (ranks > 1), wrap, and re-insert the particles that left their tile
+  // what a mover meets on each side of this rank: itself (periodic wrap), another rank (already
+  // migrated), or a physical wall with the species boundary condition of the config
+  PartBc part_bc() const {
+    PartBc bc;
+    for (int d = 0; d < 3; d++)
+      for (int sd = 0; sd < 2; sd++) {
+        const int nb = (d < dim) ? neigh[2 * d + sd] : cfg.rank;
+        int t = PBC_NONE;
+        if (nb == cfg.rank) t = PBC_WRAP;
+        else if (nb < 0) t = (cfg.part_bc[sd][d] == OSGPU_PBC_SPECULAR) ? PBC_SPECULAR : PBC_ABSORB;
+        bc.t[sd][d] = t;
+      }
+    return bc;
+  }
+
   int species_update_boundary(int id) override {  // update_boundary_species (spec/os-spec-boundary.f03:1099-1232)
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
     if (!s.movers_pending) return OSGPU_OK;
-    int wrap[3] = {0, 0, 0};
-    for (int d = 0; d < dim; d++) wrap[d] = (neigh[2 * d] == cfg.rank && neigh[2 * d + 1] == cfg.rank);
     if (multi) OSGPU_TRY(migrate(s));
-    OSGPU_TRY(movers_route<T>(s.mv, g, tl, wrap, s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, st, &launches));
+    OSGPU_TRY(movers_route<T>(s.mv, g, tl, part_bc(), s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, st, &launches));
     OSGPU_TRY(ctl_read(h_pin, d_err, sizeof(int)));
     OSGPU_TRY(ctl_sync());
     const int f = h_pin[0];
@@ -1211,6 +1325,16 @@ int osgpu_species_upload_begin(osgpu_sim *h, int id, int64_t np, const int32_t *
   return h->impl->species_upload_begin(id, np, ix, x, p, q, (const long long *)tag);
 }
 int osgpu_species_upload_end(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_upload_end(id); }
+int osgpu_move_window(osgpu_sim *h, const int32_t *nmove) {
+  H_CHECK(h);
+  if (!nmove) { osgpu::set_error("move_window: nmove is null"); return OSGPU_ERR_INVALID; }
+  return h->impl->move_window(nmove);
+}
+int osgpu_species_inject(osgpu_sim *h, int id, int64_t np, const int32_t *ix, const void *x, const void *p,
+                         const void *q, const int64_t *tag) {
+  H_CHECK(h);
+  return h->impl->species_inject(id, np, ix, x, p, q, (const long long *)tag);
+}
 int osgpu_current_zero(osgpu_sim *h) { H_CHECK(h); return h->impl->current_zero(); }
 int osgpu_species_push(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_push(id); }
 int osgpu_species_update_boundary(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_update_boundary(id); }

@@ -29,7 +29,7 @@ class Config(C.Structure):
         ("dx", C.c_double * 3), ("dt", C.c_double),
         ("node_dims", C.c_int32 * 3), ("node_coords", C.c_int32 * 3), ("periodic", C.c_int32 * 3),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32), ("smooth_order", C.c_int32),
-        ("no_tags", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("no_tags", C.c_int32), ("part_bc", (C.c_int32 * 3) * 2),
     ]
 
 
@@ -68,6 +68,8 @@ def load():
     L.osgpu_species_push.argtypes = [vp, C.c_int]
     L.osgpu_species_update_boundary.argtypes = [vp, C.c_int]
     L.osgpu_current_zero.argtypes = [vp]
+    L.osgpu_move_window.argtypes = [vp, vp]
+    L.osgpu_species_inject.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
     L.osgpu_fields_upload.argtypes = [vp, vp, vp]
     L.osgpu_fields_download.argtypes = [vp, vp, vp]
     L.osgpu_current_upload.argtypes = [vp, vp]
@@ -139,5 +141,5 @@ EXPORTS = [
     "osgpu_host_alloc", "osgpu_host_free", "osgpu_vadvance_deposit", "osgpu_current_set_smooth",
     "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
-    "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld",
+    "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

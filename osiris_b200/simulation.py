@@ -96,6 +96,15 @@ class Species:
             out = {k: v[o] for k, v in out.items()}
         return out
 
+    def inject(self, ix, x, p, q, tag=None):
+        """New particles (reference layout, ix local to this rank) join the species"""
+        dt = self.sim.dtype
+        ix = np.ascontiguousarray(ix, np.int32)
+        x, p, q = (np.ascontiguousarray(a, dt) for a in (x, p, q))
+        tag = None if tag is None else np.ascontiguousarray(tag, np.int64)
+        check(self.sim._L.osgpu_species_inject(self.sim._h, self.sp_id, q.shape[0], ptr(ix), ptr(x), ptr(p), ptr(q),
+                                               ptr(tag)))
+
     def push(self):
         """push_species (spec/os-species.f03:1461-1520): advance + deposit this species alone; its
         current is added to J (zero it first with sim.jay.zero())."""
@@ -221,7 +230,7 @@ class Simulation:
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
                  node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None,
-                 emf_smooth=None):
+                 emf_smooth=None, part_bc=None):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
@@ -250,6 +259,12 @@ class Simulation:
         cfg.dt = self.dt
         cfg.rank, cfg.nranks, cfg.device, cfg.smooth_order = self.no_co.rank, self.no_co.nranks, device, smooth_order
         cfg.no_tags = 0 if add_tag else 1  # species{add_tag} (spec/os-spec-define.f03:431)
+        # species boundary condition at physical walls, ([lower per axis], [upper per axis]) of
+        # "absorbing" | "specular"; a moving window along x is (["absorbing", ..], ["specular", ..])
+        if part_bc is not None:
+            for s_ in range(2):
+                for d in range(dim):
+                    cfg.part_bc[s_][d] = {"absorbing": 0, "specular": 1}[part_bc[s_][d]]
         self.add_tag = bool(add_tag)
         self._cfg = cfg
         self._h = C.c_void_p()
@@ -287,6 +302,12 @@ class Simulation:
         ene = np.zeros(max(1, self.nspecies), np.float64)
         check(self._L.osgpu_step(self._h, int(nsteps), ene.ctypes.data_as(C.POINTER(C.c_double))))
         return ene
+
+    def move_window(self, nmove):
+        """emf%move_window + part%move_window (os-simulation.f03:529-548) by nmove[dim] cells"""
+        nm = np.zeros(3, np.int32)
+        nm[:self.dim] = nmove
+        check(self._L.osgpu_move_window(self._h, ptr(nm)))
 
     def phase_times_ms(self):
         out = np.zeros(8, np.float64)

@@ -7,7 +7,8 @@ from oracle.bindings import Oracle, aligned
 
 
 class OracleSim:
-    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None, emf_smooth=None):
+    def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None, emf_smooth=None,
+                 periodic=None, part_bc=None):
         self.orc = Oracle(precision)
         self.dtype = self.orc.dtype
         self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
@@ -19,22 +20,31 @@ class OracleSim:
         self.b = np.zeros(sh(self.gc_emf), self.dtype)
         self.j = np.zeros(sh(self.gc_jay), self.dtype)
         self.species = []
+        # periodic[d]; part_bc = ([lower per axis], [upper per axis]) of "absorbing" | "specular" on the others
+        self.periodic = list(periodic) if periodic is not None else [True] * dim
+        self.part_bc = part_bc if part_bc is not None else (["absorbing"] * dim, ["absorbing"] * dim)
         self.smooth = smooth  # (order[dim], max_order, scoef[dim, 2 max_order + 1]) from Oracle.smooth_setup
         self.emf_smooth = emf_smooth  # the same for el_mag_fld{ smooth_type = "stand" }
         self.e_part, self.b_part = self.e, self.b
         # particles use dt rounded to their precision (spec/os-spec-vpush.f03:374)
         self.dtp = float(self.dtype(self.dt))
 
-    def add_species(self, rqm, ix, x, p, q):
+    def add_species(self, rqm, ix, x, p, q, tag=None):
         sp = dict(rqm=float(rqm), ix=np.ascontiguousarray(ix, np.int32).copy(),
                   x=np.ascontiguousarray(x, self.dtype).copy(), p=np.ascontiguousarray(p, self.dtype).copy(),
                   q=np.ascontiguousarray(q, self.dtype).copy())
+        if tag is not None:
+            sp["tag"] = np.asarray(tag, np.int64).copy()
         self.species.append(sp)
         return sp
 
+    def _paxes(self):
+        return [d for d in range(self.dim) if self.periodic[d]]
+
     def emf_update_boundary(self):
-        self.orc.update_periodic(self.dim, self.e, self.nx, self.gc_emf, "replace")
-        self.orc.update_periodic(self.dim, self.b, self.nx, self.gc_emf, "replace")
+        # physical walls of a moving window (p_bc_move_c) do nothing to the fields
+        self.orc.update_periodic(self.dim, self.e, self.nx, self.gc_emf, "replace", axes=self._paxes())
+        self.orc.update_periodic(self.dim, self.b, self.nx, self.gc_emf, "replace", axes=self._paxes())
 
     def emf_update_particle_fld(self):
         """update_particle_fld (emf/os-emf.f03:1065-1150) with smooth_type "stand" """
@@ -59,11 +69,34 @@ class OracleSim:
         return np.array(ene)
 
     def particles_update_boundary(self):
+        bc = tuple(["periodic" if self.periodic[d] else self.part_bc[sd][d] for d in range(self.dim)] for sd in range(2))
         for sp in self.species:
-            self.orc.particles_periodic(self.dim, sp["ix"], self.nx)
+            if all(self.periodic):
+                self.orc.particles_periodic(self.dim, sp["ix"], self.nx)
+                continue
+            keep = self.orc.particles_bc(self.dim, sp["ix"], sp["x"], sp["p"], self.nx, bc)
+            for k in ("ix", "x", "p", "q", "tag"):
+                if k in sp:
+                    sp[k] = np.ascontiguousarray(sp[k][keep])
 
     def current_update_boundary(self):
-        self.orc.update_periodic(self.dim, self.j, self.nx, self.gc_jay, "add")
+        self.orc.update_periodic(self.dim, self.j, self.nx, self.gc_jay, "add", axes=self._paxes())
+
+    def move_window(self, nmove):
+        """emf%move_window + part%move_window (os-simulation.f03:529-548)"""
+        self.orc.move_window_vdf(self.dim, self.b, self.nx, self.gc_emf, nmove)
+        self.orc.move_window_vdf(self.dim, self.e, self.nx, self.gc_emf, nmove)
+        for sp in self.species:
+            sp["ix"] -= np.asarray(nmove, np.int32)[None, :self.dim]
+        self.particles_update_boundary()
+
+    def inject(self, isp, ix, x, p, q, tag=None):
+        sp = self.species[isp]
+        sp["ix"] = np.ascontiguousarray(np.concatenate([sp["ix"], np.asarray(ix, np.int32)]))
+        for k, v in (("x", x), ("p", p), ("q", q)):
+            sp[k] = np.ascontiguousarray(np.concatenate([sp[k], np.asarray(v, self.dtype)]))
+        if "tag" in sp:
+            sp["tag"] = np.concatenate([sp["tag"], np.asarray(tag, np.int64)])
 
     def current_smooth(self):
         if self.smooth is not None:

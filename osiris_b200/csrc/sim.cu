@@ -660,7 +660,10 @@ template <typename T> struct Sim final : SimBase {
       std::vector<long long> ooff(tl.ntile + 1);
       long long np = 0;
       for (int t = 0; t < tl.ntile; t++) { ooff[t] = np; np += cnt[t]; }
-      if (np == 0) continue;
+      if (np == 0) {  // (still collective across ranks)
+        OSGPU_TRY(species_update_boundary((int)i));
+        continue;
+      }
       const size_t bix = sizeof(int) * dim * np, bx_ = sizeof(T) * dim * np, bp = sizeof(T) * 3 * np, bq = sizeof(T) * np;
       const size_t btag = cfg.no_tags ? 0 : sizeof(long long) * np, boff = sizeof(long long) * (tl.ntile + 1);
       const size_t al = 256;
@@ -716,7 +719,7 @@ template <typename T> struct Sim final : SimBase {
     if (have < 0) return OSGPU_ERR_CUDA;
     OSGPU_TRY(movers_inject<T>(in, (int)np, have, g, s.mv, 0, st, &launches));
     s.movers_pending = true;
-    OSGPU_TRY(species_update_boundary(id));
+    OSGPU_TRY(species_boundary(id, false));  // rank-local: ranks inject different amounts, or nothing
     OSGPU_CUDA(cudaStreamSynchronize(st));  // the host arrays and the staging area are free again
     return OSGPU_OK;
   }
@@ -1022,11 +1025,18 @@ template <typename T> struct Sim final : SimBase {
     return bc;
   }
 
-  int species_update_boundary(int id) override {  // update_boundary_species (spec/os-spec-boundary.f03:1099-1232)
+  int species_update_boundary(int id) override { return species_boundary(id, true); }
+  // update_boundary_species (spec/os-spec-boundary.f03:1099-1232).  with_migration = false keeps the
+  // call local to this rank (no collective): the movers are known to lie inside 1..nx (injection).
+  int species_boundary(int id, bool with_migration) {
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
-    if (!s.movers_pending) return OSGPU_OK;
-    if (multi) OSGPU_TRY(migrate(s));
+    if (!s.movers_pending) {
+      if (!(multi && with_migration)) return OSGPU_OK;
+      // nothing of this rank leaves, but the neighbours' exchange is collective: take part with an empty list
+      OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
+    }
+    if (multi && with_migration) OSGPU_TRY(migrate(s));
     OSGPU_TRY(movers_route<T>(s.mv, g, tl, part_bc(), s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, st, &launches));
     OSGPU_TRY(ctl_read(h_pin, d_err, sizeof(int)));
     OSGPU_TRY(ctl_sync());

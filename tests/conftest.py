@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout), so a stuck collective cannot stall the suite")
 
 
 def _gpu_count():

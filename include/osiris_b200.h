@@ -87,6 +87,10 @@ int osgpu_cart_neighbors(int dim, const int32_t *dims, const int32_t *periodic, 
  * inclusive.  mode 0 = replace (E,B), 1 = add (J).  out = {send_lo0, send_lo1, send_up0, send_up1,
  * recv_lo0, recv_lo1, recv_up0, recv_up1} */
 int osgpu_exchange_ranges(int nx, int gcl, int gcu, int mode, int32_t *out8);
+/* the same for the exchange that follows a window move of nx_move cells along the axis: the replace
+ * ranges slide down so the upper neighbour also refreshes the cells the shift pulled out of stale
+ * guard cells (nx_move argument of isend_vdf / irecv_vdf, vdf/os-vdf-comm.f90:770-776, 880-887) */
+int osgpu_exchange_ranges_move(int nx, int gcl, int gcu, int mode, int nx_move, int32_t *out8);
 /* minimum guard cells the particles need for an interpolation order
  * (particles/os-particles.f03:329-346) merged with the Yee solver's (1,2)
  * (emf/solver/os-emf-solver-yee.f03:458-468): out = {lower, upper} */

@@ -649,6 +649,7 @@ template <typename T> struct Sim final : SimBase {
     Field3<T> tmp{{jtmp, jtmp + g.vol, jtmp + 2 * g.vol}};
     OSGPU_TRY(shift_field<T>(g, B, tmp, bx, nm, st, &launches));
     OSGPU_TRY(shift_field<T>(g, E, tmp, bx, nm, st, &launches));
+    for (int d = 0; d < 3; d++) move_pending[d] += nm[d];  // the next E/B guard exchange slides its ranges
     const Shift3 sh{{nm[0], nm[1], nm[2]}};
     for (size_t i = 0; i < sp.size(); i++) {
       Species &s = sp[i];
@@ -819,6 +820,9 @@ template <typename T> struct Sim final : SimBase {
   // ---------------------------------------------------------------------------------------
   // guard cells: in-rank periodic copy/fold, or slab exchange with the neighbours.
   // ranges: vdf/os-vdf-comm.f90:756-784 (see osgpu_exchange_ranges)
+  // cells the window moved since the last E/B guard exchange (consumed by emf_update_boundary)
+  int move_pending[3] = {0, 0, 0};
+  int nx_move_of(int d, int mode) const { return mode == 0 ? move_pending[d] : 0; }
   int update_guards(T *const *comps, int nc, int mode) {
     for (int d = 0; d < dim; d++) {
       const int lo = neigh[2 * d], up = neigh[2 * d + 1];
@@ -828,7 +832,7 @@ template <typename T> struct Sim final : SimBase {
       }
       if (lo < 0 && up < 0) continue;
       int r[8];
-      osgpu_exchange_ranges(g.nx[d], g.ul[d], g.uu[d], mode, r);
+      osgpu_exchange_ranges_move(g.nx[d], g.ul[d], g.uu[d], mode, nx_move_of(d, mode), r);
       auto pad = [&](int cell) { return cell - 1 + g.gl[d]; };
       const long long vs_lo = slab_volume(g, d, pad(r[0]), pad(r[1])) * nc;  // to the lower neighbour
       const long long vs_up = slab_volume(g, d, pad(r[2]), pad(r[3])) * nc;  // to the upper neighbour
@@ -846,7 +850,9 @@ template <typename T> struct Sim final : SimBase {
   }
   int emf_update_boundary() override {
     T *comps[6] = {E.c[0], E.c[1], E.c[2], B.c[0], B.c[1], B.c[2]};
-    return update_guards(comps, 6, 0);
+    const int rc = update_guards(comps, 6, 0);
+    for (int d = 0; d < 3; d++) move_pending[d] = 0;
+    return rc;
   }
   int current_update_boundary() override {
     T *comps[3] = {J.c[0], J.c[1], J.c[2]};
@@ -1248,11 +1254,18 @@ int osgpu_cart_neighbors(int dim, const int32_t *dims, const int32_t *periodic, 
   return OSGPU_OK;
 }
 int osgpu_exchange_ranges(int nx, int gcl, int gcu, int mode, int32_t *o) {
+  return osgpu_exchange_ranges_move(nx, gcl, gcu, mode, 0, o);
+}
+int osgpu_exchange_ranges_move(int nx, int gcl, int gcu, int mode, int nx_move, int32_t *o) {
   if (mode == 0) {            // replace: interior cells next to the face fill the neighbour's guards
-    o[0] = 1;            o[1] = gcu;        // to lower neighbour (its upper guards)
-    o[2] = nx + 1 - gcl; o[3] = nx;         // to upper neighbour (its lower guards)
-    o[4] = 1 - gcl;      o[5] = 0;          // from lower neighbour
-    o[6] = nx + 1;       o[7] = nx + gcu;   // from upper neighbour
+    // After a window move of m cells the last m interior cells of the lower rank were shifted in from
+    // its own stale guard cells: the ranges slide down by m so the upper neighbour refreshes them too
+    // (isend_vdf / irecv_vdf with nx_move, vdf/os-vdf-comm.f90:770-776, 880-887)
+    const int m = nx_move;
+    o[0] = 1 - m;        o[1] = gcu;        // to lower neighbour (its upper guards)
+    o[2] = nx + 1 - gcl; o[3] = nx - m;     // to upper neighbour (its lower guards)
+    o[4] = 1 - gcl;      o[5] = 0 - m;      // from lower neighbour
+    o[6] = nx + 1 - m;   o[7] = nx + gcu;   // from upper neighbour
   } else {                    // add: guard + overlap range, summed on both sides
     o[0] = 1 - gcl;      o[1] = gcu;
     o[2] = nx + 1 - gcl; o[3] = nx + gcu;

@@ -53,6 +53,7 @@ def load():
     L.osgpu_cart_coords.argtypes = [C.c_int, i32p, C.c_int, i32p]
     L.osgpu_cart_neighbors.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p]
     L.osgpu_exchange_ranges.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    L.osgpu_exchange_ranges_move.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.osgpu_min_gc.argtypes = [C.c_int, i32p]
     L.osgpu_nccl_unique_id.argtypes = [vp]
     L.osgpu_init.argtypes = [C.POINTER(vp), C.POINTER(Config), vp]
@@ -142,4 +143,5 @@ EXPORTS = [
     "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
+    "osgpu_exchange_ranges_move",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -111,3 +111,30 @@ def test_loads_are_decomposition_independent():
     # lattice of inject_std: x = (2i - 1 - n)/(2n)
     assert sorted(set(np.round(whole["x"][:, 0], 6))) == [-0.25, 0.25]
     assert np.allclose(whole["q"], -0.25)
+
+
+def test_exchange_ranges_after_a_window_move():
+    """isend_vdf / irecv_vdf with nx_move (vdf/os-vdf-comm.f90:770-776, 880-887): the replace ranges slide
+    down by nx_move, the add ranges do not, and what one rank sends is what its neighbour receives"""
+    import ctypes as C
+    from osiris_b200 import lib
+    L = lib.load()
+    nx, gcl, gcu = 20, 3, 4
+    for m in (0, 1, 2):
+        r = (C.c_int32 * 8)()
+        assert L.osgpu_exchange_ranges_move(nx, gcl, gcu, 0, m, r) == 0
+        assert list(r) == [1 - m, gcu, nx + 1 - gcl, nx - m, 1 - gcl, 0 - m, nx + 1 - m, nx + gcu]
+        # lower rank's "from upper" cells c  <->  upper rank's "to lower" cells c - nx
+        assert (r[6] - nx, r[7] - nx) == (r[0], r[1])
+        # upper rank's "from lower" cells c  <->  lower rank's "to upper" cells c + nx
+        assert (r[4] + nx, r[5] + nx) == (r[2], r[3])
+        a = (C.c_int32 * 8)()
+        L.osgpu_exchange_ranges_move(nx, gcl, gcu, 1, m, a)
+        b = (C.c_int32 * 8)()
+        L.osgpu_exchange_ranges(nx, gcl, gcu, 1, b)
+        assert list(a) == list(b)
+    r0 = (C.c_int32 * 8)()
+    L.osgpu_exchange_ranges(nx, gcl, gcu, 0, r0)
+    r1 = (C.c_int32 * 8)()
+    L.osgpu_exchange_ranges_move(nx, gcl, gcu, 0, 0, r1)
+    assert list(r0) == list(r1)

@@ -50,6 +50,42 @@ class NodeConf:
         self.neighbor = [[int(nb[2 * d]), int(nb[2 * d + 1])] for d in range(dim)]
 
 
+class Space:
+    """t_space (source/os-space.f90): the part the moving window needs -- which axes move, how far
+    the window has travelled, and how many cells it moves this step.  The host keeps this object
+    (deck section `space{ xmin, xmax, if_move }`); the device is told nx_move through
+    Simulation.move_window."""
+
+    def __init__(self, xmin, xmax, if_move=None, move_vel=0.0):
+        self.x_dim = len(xmin)
+        self.x_bnd_initial = [list(map(float, xmin)), list(map(float, xmax))]
+        self.x_bnd = [list(map(float, xmin)), list(map(float, xmax))]
+        self.if_move = [bool(v) for v in (if_move if if_move is not None else [False] * self.x_dim)]
+        self.move_vel = float(move_vel)
+        self.xmoved = [0.0] * self.x_dim
+        self.total_i_moved = [0] * self.x_dim
+        self.move_num = [0] * self.x_dim
+
+    def move_boundary(self, dx, dt):
+        """move_boundary_space_global (os-space.f90:508-562): accumulate the distance travelled at c (or
+        move_vel) and move by ONE cell when it reaches dx; returns nx_move per axis."""
+        for d in range(self.x_dim):
+            self.move_num[d] = 0
+            if not self.if_move[d]:
+                continue
+            self.xmoved[d] += self.move_vel * dt if self.move_vel > 0.0 else dt
+            if self.xmoved[d] >= dx[d]:
+                self.move_num[d] = 1
+                self.xmoved[d] -= dx[d]
+                self.total_i_moved[d] += 1
+                for s_ in range(2):
+                    self.x_bnd[s_][d] = self.x_bnd_initial[s_][d] + self.total_i_moved[d] * dx[d]
+        return list(self.move_num)
+
+    def nx_move(self):
+        return list(self.move_num)
+
+
 class Species:
     """t_species (spec/os-spec-define.f03:327-549) device mirror."""
 

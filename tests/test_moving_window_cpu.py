@@ -74,3 +74,23 @@ def test_particle_boundaries(dim):
     lo = (ix[:, 0] < 1) & keep
     assert (a[lo, 0] == 1).all() and np.array_equal(pa[lo, 0], -p[lo, 0])
     assert np.array_equal(keep, (ix <= np.array(nx)).all(axis=1))
+
+
+def test_space_move_boundary():
+    """host mirror of move_boundary_space_global (os-space.f90:508-562): at most one cell per step, the
+    remainder carried, the window edge recomputed from the initial edge (no round-off drift)"""
+    from osiris_b200.simulation import Space
+    sp = Space([0.0, -3.0], [12.8, 3.0], if_move=[True, False])
+    dx, dt = [0.1, 0.2], 0.07
+    moves, t = [], 0.0
+    for n in range(1000):
+        nm = sp.move_boundary(dx, dt)
+        assert nm[1] == 0 and nm[0] in (0, 1)
+        moves.append(nm[0])
+    assert sum(moves) == sp.total_i_moved[0] == int(np.floor(1000 * dt / dx[0] + 1e-9))
+    assert abs(sp.x_bnd[0][0] - sum(moves) * dx[0]) < 1e-12 and abs(sp.x_bnd[1][0] - (12.8 + sum(moves) * dx[0])) < 1e-12
+    assert 0.0 <= sp.xmoved[0] < dx[0]
+    assert sp.x_bnd[0][1] == -3.0
+    slow = Space([0.0], [1.0], if_move=[True], move_vel=0.5)
+    n = sum(slow.move_boundary([0.1], 0.07)[0] for _ in range(200))
+    assert n == int(np.floor(200 * 0.5 * 0.07 / 0.1 + 1e-9))

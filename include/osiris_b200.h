@@ -138,7 +138,9 @@ int osgpu_species_download_async(osgpu_sim *sim, int sp_id, int32_t *ix, void *x
  * nmove[dim] = nx_move(g_space) cells (the host keeps t_space and decides when the window moves):
  * E, B slide down and are zero-filled (vdf/os-vdf.f03:56-205), every particle's ix drops by nmove
  * (spec/os-species.f03:171-229) and leavers meet migration / part_bc.  Call it before
- * osgpu_step; follow it with osgpu_species_inject for the plasma the window uncovered. */
+ * osgpu_step; follow it with osgpu_species_inject for the plasma the window uncovered.
+ * Deviation: the reference leaves the particles that dropped to cell 0 in the buffer for one more
+ * push and removes them at the next update_boundary; here they meet the wall at once. */
 int osgpu_move_window(osgpu_sim *sim, const int32_t *nmove);
 /* np new particles (host arrays in the reference layout, ix local to this rank, inside 1..nx) join
  * the species: the inject() of move_window_species (spec/os-species.f03:218-226) with the particles

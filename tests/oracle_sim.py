@@ -8,7 +8,7 @@ from oracle.bindings import Oracle, aligned
 
 class OracleSim:
     def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None, emf_smooth=None,
-                 periodic=None, part_bc=None):
+                 periodic=None, part_bc=None, window_order="device"):
         self.orc = Oracle(precision)
         self.dtype = self.orc.dtype
         self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
@@ -23,6 +23,11 @@ class OracleSim:
         # periodic[d]; part_bc = ([lower per axis], [upper per axis]) of "absorbing" | "specular" on the others
         self.periodic = list(periodic) if periodic is not None else [True] * dim
         self.part_bc = part_bc if part_bc is not None else (["absorbing"] * dim, ["absorbing"] * dim)
+        # "device": the particles a window move pushes out meet the wall / migration at once (what
+        # osgpu_move_window does); "reference": they stay in cell 0 for one more push and are removed by the
+        # next update_boundary (move_window_species only lowers ix, spec/os-species.f03:171-229) -- needs one
+        # more lower guard cell on the moving axis, as the reference allocates (emf/os-emf.f03:684-688)
+        self.window_order = window_order
         self.smooth = smooth  # (order[dim], max_order, scoef[dim, 2 max_order + 1]) from Oracle.smooth_setup
         self.emf_smooth = emf_smooth  # the same for el_mag_fld{ smooth_type = "stand" }
         self.e_part, self.b_part = self.e, self.b
@@ -88,7 +93,8 @@ class OracleSim:
         self.orc.move_window_vdf(self.dim, self.e, self.nx, self.gc_emf, nmove)
         for sp in self.species:
             sp["ix"] -= np.asarray(nmove, np.int32)[None, :self.dim]
-        self.particles_update_boundary()
+        if self.window_order == "device":
+            self.particles_update_boundary()
 
     def inject(self, isp, ix, x, p, q, tag=None):
         sp = self.species[isp]

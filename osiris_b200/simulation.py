@@ -19,7 +19,7 @@ from . import lib as _lib
 from .lib import Config, check, ptr
 
 
-def min_gc(order, smooth_order=0, moving=()):
+def min_gc(order, smooth_order=0):
     """Guard cells (lower[D]-like scalar pair) the reference would allocate for E/B and J:
     particles need (order, order+1) (particles/os-particles.f03:329-346), Yee (1,2)
     (emf/solver/os-emf-solver-yee.f03:458-468), + smoothing order on both sides
@@ -27,6 +27,14 @@ def min_gc(order, smooth_order=0, moving=()):
     out = (C.c_int32 * 2)()
     check(_lib.load().osgpu_min_gc(order, out))
     return int(out[0]) + smooth_order, int(out[1]) + smooth_order
+
+
+def min_gc_axes(dim, order, smooth_order=0, if_move=None):
+    """The same per axis, ([lower], [upper]): an axis the window moves along gets one more lower guard
+    cell (emf/os-emf.f03:684-688, current/os-current-define.f03:194-197)."""
+    lo, up = min_gc(order, smooth_order)
+    mv = [bool(v) for v in (if_move if if_move is not None else [False] * dim)]
+    return [lo + (1 if mv[d] else 0) for d in range(dim)], [up] * dim
 
 
 class NodeConf:
@@ -266,7 +274,7 @@ class Simulation:
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
                  node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None,
-                 emf_smooth=None, part_bc=None):
+                 emf_smooth=None, part_bc=None, if_move=None):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
@@ -275,9 +283,9 @@ class Simulation:
         self.dt = float(dt)
         if emf_smooth is not None:
             smooth_order = max(smooth_order, emf_smooth.smooth_order())
-        lo, up = min_gc(self.order, smooth_order)
-        self.gc_emf = gc_emf if gc_emf is not None else ([lo] * dim, [up] * dim)
-        self.gc_jay = gc_jay if gc_jay is not None else ([lo] * dim, [up] * dim)
+        glo, gup = min_gc_axes(dim, self.order, smooth_order, if_move)
+        self.gc_emf = gc_emf if gc_emf is not None else (list(glo), list(gup))
+        self.gc_jay = gc_jay if gc_jay is not None else (list(glo), list(gup))
         if smooth is not None and gc_jay is None:  # setup of t_current (current/os-current-define.f03:192-205)
             self.gc_jay = smooth.gc_num(self.gc_jay)
         self.no_co = node_conf if node_conf is not None else NodeConf(dim)

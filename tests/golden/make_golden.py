@@ -19,8 +19,8 @@ from oracle.bindings import RefSimd, aligned  # noqa: E402
 from oracle_sim import random_case  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CASES = [(2, 1, "f32"), (2, 2, "f32"), (3, 1, "f32"), (3, 2, "f32"), (3, 3, "f32"), (2, 4, "f32"),
-         (2, 2, "f64"), (3, 2, "f64"), (3, 4, "f64")]
+# every dimension x spline order x precision the pusher is instantiated for
+CASES = [(d, o, p) for p in ("f32", "f64") for d in (2, 3) for o in (1, 2, 3, 4)]
 SHAPES = {2: [21, 18], 3: [11, 10, 9]}
 DX = {2: [0.1, 0.12], 3: [0.1, 0.12, 0.09]}
 

@@ -49,3 +49,29 @@ def test_kernel_statements_match_oracle(emu, dim, order, prec):
     assert np.array_equal(ix, ix2) and np.array_equal(x, x2) and np.array_equal(u, u2)
     assert np.abs(j - j2).max() <= (2e-6 if prec == "f32" else 1e-14) * np.abs(j).max()
     assert abs(ene_e - ene_o) <= 1e-12 * abs(ene_o)
+
+
+def test_kernel_statements_match_reference_golden_vectors(emu):
+    """the same host build of the device statements against the vectors the reference's own compiled
+    kernels produced (tests/golden): x, p, ix bit-identical, J to the summation-order tolerance the GPU
+    test uses"""
+    import glob
+    files = sorted(glob.glob(os.path.join(HERE, "golden", "vadv_*.npz")))
+    assert len(files) == 16
+    for f in files:
+        g = np.load(f)
+        dim, order = int(g["dim"]), int(g["order"])
+        prec = "f32" if g["x"].dtype == np.float32 else "f64"
+        ix, x, u, j = g["ix"].copy(), g["x"].copy(), g["u"].copy(), np.zeros_like(g["e"])
+        q, e, b = np.ascontiguousarray(g["q"]), np.ascontiguousarray(g["e"]), np.ascontiguousarray(g["b"])
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        esz = np.ascontiguousarray(e.shape[::-1][1:1 + dim], np.int32)
+        off = np.ascontiguousarray(g["gcl"], np.int32)
+        nxa, dxa = np.ascontiguousarray(g["nx"], np.int32), np.ascontiguousarray(g["dx"], np.float64)
+        ene = emu.emul_advance_deposit(dim, order, x.itemsize, p(ix), p(x), p(u), p(q), C.c_long(q.shape[0]),
+                                       C.c_double(float(g["rqm"])), p(e), p(b), p(esz), p(off), p(j), p(esz), p(off),
+                                       p(nxa), p(dxa), C.c_double(float(g["dt"])))
+        assert np.array_equal(ix, g["ix_out"]), f
+        assert np.array_equal(x, g["x_out"]) and np.array_equal(u, g["u_out"]), f
+        assert np.abs(j - g["j_out"]).max() <= (1e-5 if prec == "f32" else 1e-12) * np.abs(g["j_out"]).max(), f
+        assert abs(ene - float(g["ene_out"])) <= (1e-5 if prec == "f32" else 1e-11) * abs(float(g["ene_out"])), f

@@ -16,8 +16,8 @@ from osiris_b200.simulation import NodeConf
 
 
 class DecompOracleSim(OracleSim):
-    def __init__(self, dim, order, nx_local, dx, dt, precision, node_dims, rank, periodic=None, part_bc=None):
-        super().__init__(dim, order, nx_local, dx, dt, precision, periodic=periodic, part_bc=part_bc)
+    def __init__(self, dim, order, nx_local, dx, dt, precision, node_dims, rank, periodic=None, part_bc=None, **kw):
+        super().__init__(dim, order, nx_local, dx, dt, precision, periodic=periodic, part_bc=part_bc, **kw)
         self.no_co = NodeConf(dim, node_dims, self.periodic, rank)
         self.rank = rank
         self.L = lib.load()

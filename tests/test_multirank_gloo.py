@@ -195,3 +195,61 @@ def test_moving_window_two_ranks_reproduce_one(tmp_path, dim, node_dims):
     assert np.array_equal(tags[o], ref["tag"][o1])      # the same particles were absorbed, kept and injected
     assert np.array_equal(gix[o], ref["ix"][o1])
     assert np.abs(x[o] - ref["x"][o1]).max() < 1e-10 and np.abs(p[o] - ref["p"][o1]).max() < 1e-10
+
+
+# ---- smoothing across two ranks ---------------------------------------------------------------------
+def _smooth_setup(dim):
+    from oracle.bindings import Oracle
+    return Oracle("f64").smooth_setup(dim, ["compensated"] * dim, [2] * dim)
+
+
+def _smooth_worker(rank, world, port, dim, node_dims, gnx, nsteps, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    from decomp_oracle import DecompOracleSim
+    from osiris_b200.loads import lattice_species
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    nxl = [gnx[d] // node_dims[d] for d in range(dim)]
+    setup = _smooth_setup(dim)
+    gc = ([2 + 2] * dim, [3 + 2] * dim)  # interpolation guard cells + smoothing order (emf/os-emf.f03:702-706)
+    s = DecompOracleSim(dim, 2, nxl, [0.5] * dim, 0.2, "f64", node_dims, rank, gc_emf=gc, gc_jay=gc, smooth=setup,
+                        emf_smooth=setup)
+    off = [s.no_co.coords[d] * nxl[d] for d in range(dim)]
+    part = lattice_species(nxl, [2] * dim, np.float64, uth=(0.3, 0.3, 0.3), global_nx=gnx, offset=off)
+    s.add_species(-1.0, part["ix"], part["x"], part["p"], part["q"], tag=np.zeros(len(part["q"]), np.int64))
+    s.iter(nsteps)
+    gl = s.gc_emf[0]
+    inner = tuple(slice(gl[d], gl[d] + nxl[d]) for d in reversed(range(dim)))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), e=s.e[inner], b=s.b[inner], off=np.array(off))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dim,node_dims", [(2, [2, 1]), (2, [1, 2])])
+def test_smoothing_two_ranks_reproduce_one(tmp_path, dim, node_dims):
+    """current smoothing and field smoothing for the particles on a decomposed grid: every rank filters
+    its own block, guard cells included, after the guard-cell exchange; with the guard cells the
+    reference allocates (+ order) no second exchange is needed and the result is the single-rank one"""
+    from oracle_sim import OracleSim
+    from osiris_b200.loads import lattice_species
+    gnx = [16, 16]
+    nsteps = 5
+    mp.spawn(_smooth_worker, args=(2, _free_port(), dim, node_dims, gnx, nsteps, str(tmp_path)), nprocs=2, join=True)
+    setup = _smooth_setup(dim)
+    gc = ([4] * dim, [5] * dim)
+    s = OracleSim(dim, 2, gnx, [0.5] * dim, 0.2, "f64", gc_emf=gc, gc_jay=gc, smooth=setup, emf_smooth=setup)
+    part = lattice_species(gnx, [2] * dim, np.float64, uth=(0.3, 0.3, 0.3))
+    s.add_species(-1.0, part["ix"], part["x"], part["p"], part["q"])
+    s.iter(nsteps)
+    gl = s.gc_emf[0]
+    inner = tuple(slice(gl[d], gl[d] + gnx[d]) for d in reversed(range(dim)))
+    e1, b1 = s.e[inner], s.b[inner]
+    for r in range(2):
+        g = np.load(tmp_path / f"rank{r}.npz")
+        off = g["off"]
+        nxl = [gnx[d] // node_dims[d] for d in range(dim)]
+        sl = tuple(slice(off[d], off[d] + nxl[d]) for d in reversed(range(dim)))
+        assert np.abs(g["e"] - e1[sl]).max() < 1e-11 * np.abs(e1).max()
+        assert np.abs(g["b"] - b1[sl]).max() < 1e-11 * max(np.abs(b1).max(), 1e-30)

@@ -75,3 +75,31 @@ def test_kernel_statements_match_reference_golden_vectors(emu):
         assert np.array_equal(x, g["x_out"]) and np.array_equal(u, g["u_out"]), f
         assert np.abs(j - g["j_out"]).max() <= (1e-5 if prec == "f32" else 1e-12) * np.abs(g["j_out"]).max(), f
         assert abs(ene - float(g["ene_out"])) <= (1e-5 if prec == "f32" else 1e-11) * abs(float(g["ene_out"])), f
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_kernel_statements_on_branch_inputs(emu, dim, order, prec):
+    """the device statements on the inputs that sit on the branches (cell faces, +-0, particles at rest,
+    gamma ~ 100, multi-face crossings at the Courant limit, outermost cells): bit-identical to the oracle,
+    which test_oracle_vs_ref pins bit-exact to the reference's kernels on the very same inputs"""
+    from test_oracle_vs_ref import _edge_case, SHAPES as RSHAPES, DX as RDX
+    orc = Oracle(prec)
+    c = _edge_case(dim, order, prec, 1000 + dim + 4 * order)
+    nx = RSHAPES[dim]
+    dtmax = 1.0 / np.sqrt(sum(1.0 / h ** 2 for h in RDX[dim]))
+    dtp = float(c["x"].dtype.type(0.999 * dtmax))
+    ix, x, u, j = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+    ene_o = orc.advance_deposit(dim, order, ix, x, u, c["q"], -1.0, c["e"], c["b"], c["gc"], j, c["gc"], RDX[dim], dtp)
+    ix2, x2, u2, j2 = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    esz = np.ascontiguousarray(c["e"].shape[::-1][1:1 + dim], np.int32)
+    off = np.ascontiguousarray(c["gc"][0], np.int32)
+    nxa, dxa = np.ascontiguousarray(nx, np.int32), np.ascontiguousarray(RDX[dim], np.float64)
+    ene_e = emu.emul_advance_deposit(dim, order, x2.itemsize, p(ix2), p(x2), p(u2), p(c["q"]), C.c_long(c["q"].shape[0]),
+                                     C.c_double(-1.0), p(c["e"]), p(c["b"]), p(esz), p(off), p(j2), p(esz), p(off),
+                                     p(nxa), p(dxa), C.c_double(dtp))
+    assert np.array_equal(ix, ix2) and np.array_equal(x, x2) and np.array_equal(u, u2)
+    assert np.abs(j - j2).max() <= (4e-6 if prec == "f32" else 1e-13) * np.abs(j).max()
+    assert abs(ene_e - ene_o) <= 1e-11 * abs(ene_o)

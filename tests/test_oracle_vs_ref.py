@@ -98,3 +98,56 @@ def test_oracle_matches_committed_golden_vectors():
         assert np.array_equal(ix, g["ix_out"]) and np.array_equal(x, g["x_out"]) and np.array_equal(u, g["u_out"]), f
         assert np.abs(j - g["j_out"]).max() <= (1e-6 if prec == "f32" else 1e-14) * np.abs(g["j_out"]).max(), f
         assert abs(ene - float(g["ene_out"])) <= 1e-6 * abs(float(g["ene_out"]))
+
+
+def _edge_case(dim, order, prec, seed):
+    """inputs that sit on the branches of the statement: particles exactly on cell faces and cell
+    centres, at rest, ultra-relativistic, with dt/dx at the Courant limit, in the outermost cells, and
+    pairs that cross one, two or three faces in one step"""
+    dt_ = np.float32 if prec == "f32" else np.float64
+    rng = np.random.default_rng(seed)
+    c = random_case(dim, order, prec, SHAPES[dim], ppc=6, seed=seed)
+    n = c["q"].shape[0]
+    x, u, ix = c["x"], c["u"], c["ix"]
+    k = n // 8
+    x[0 * k:1 * k] = dt_(-0.5)                                    # on the lower face (inclusive side)
+    x[1 * k:2 * k] = np.nextafter(dt_(0.5), dt_(0))               # just below the upper face
+    x[2 * k:3 * k] = dt_(0.0)                                     # the half-cell switch h = (x < 0)
+    x[3 * k:4 * k, 0] = -dt_(0.0)                                 # negative zero
+    u[4 * k:5 * k] = 0                                            # at rest
+    u[5 * k:6 * k] *= dt_(200.0)                                  # gamma ~ 100
+    u[6 * k:7 * k] = (rng.choice([-1.0, 1.0], (k, 3)) * 30.0).astype(dt_)   # v ~ c on every axis: multi-face crossings
+    for d in range(dim):                                          # outermost cells: stencil reaches the last guard cell
+        ix[7 * k:, d] = rng.choice([1, SHAPES[dim][d]], n - 7 * k)
+    return c
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_oracle_bit_exact_vs_reference_on_branch_inputs(dim, order, prec):
+    """the same pin as above on inputs chosen to hit every branch: trim at exactly +-1/2, the
+    half-point switch at +-0, particles at rest, gamma ~ 100, one/two/three face crossings per step at
+    the largest dt the Yee solver allows, and the outermost cells"""
+    if not RefSimd.available("avx2", prec):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    al = lambda a: (lambda r: (r.__setitem__(Ellipsis, a), r)[1])(aligned(a.shape, a.dtype))
+    ref, orc = RefSimd("avx2", prec), Oracle(prec)
+    for seed in range(3):
+        c = _edge_case(dim, order, prec, 1000 + 17 * seed + dim + 4 * order)
+        dtmax = 1.0 / np.sqrt(sum(1.0 / h ** 2 for h in DX[dim]))
+        dt = float(c["x"].dtype.type(0.999 * dtmax))
+        ix, x, u, q, e, b = (al(c[k]) for k in ("ix", "x", "u", "q", "e", "b"))
+        j = aligned(e.shape, e.dtype)
+        ene_r = ref.advance_deposit(dim, order, ix, x, u, q, -1.0, e, b, c["gc"], j, c["gc"], DX[dim], dt)
+        ix2, x2, u2, j2 = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+        ene_o = orc.advance_deposit(dim, order, ix2, x2, u2, c["q"], -1.0, c["e"], c["b"], c["gc"], j2, c["gc"],
+                                    DX[dim], dt)
+        assert np.array_equal(np.array(ix), ix2), seed
+        assert np.array_equal(np.array(x), x2) and np.array_equal(np.array(u), u2), seed
+        crossed = (np.array(ix) != c["ix"]).sum(axis=1)
+        assert (crossed >= 2).any() and (crossed == 0).any()      # the multi-face branches were taken
+        if not (prec == "f32" and dim == 3 and order >= 3):       # os-spec-current-avx2.c:1098,1120
+            tol = 0.0 if (prec == "f32" or dim == 2) else 1e-14
+            assert np.abs(np.array(j) - j2).max() <= tol * np.abs(j2).max(), seed
+        assert abs(ene_r - ene_o) <= (1e-6 if prec == "f32" else 1e-13) * abs(ene_r)

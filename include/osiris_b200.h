@@ -57,8 +57,8 @@ typedef struct osgpu_config {
   int32_t node_dims[OSGPU_MAX_DIM];   /* ranks per axis (1,1,1 on a single GPU)          */
   int32_t node_coords[OSGPU_MAX_DIM]; /* this rank's cartesian coordinates               */
   int32_t periodic[OSGPU_MAX_DIM];    /* periodic axes                                   */
-  int32_t rank;       /* NCCL rank = cartesian rank, x fastest (mpi_cart_create order is */
-  int32_t nranks;     /* reproduced by osgpu_cart_rank)                                  */
+  int32_t rank;       /* NCCL rank of this process = its rank in the host's communicator  */
+  int32_t nranks;     /* (t_node_conf%my_aid - 1, os-nconf.f03:540); see `topology`       */
   int32_t device;     /* CUDA device ordinal, -1 = rank % device_count                   */
   int32_t smooth_order; /* current smoothing passes folded into gc (0 = none)            */
   int32_t no_tags;    /* 1: particles carry no tag (species{add_tag} off, the reference's default,
@@ -69,19 +69,34 @@ typedef struct osgpu_config {
    * conditions at such walls are NOT applied (that is what a moving window needs, p_bc_move_c;
    * conducting / open walls are SURVEY.md 8f row 3). */
   int32_t part_bc[2][OSGPU_MAX_DIM];
+  /* How ranks map to node_coords (node_conf{topology}, os-nconf.f03:461-482):
+   *   OSGPU_TOPO_MPI  (0, the reference's default "mpi"): row-major, LAST axis fastest -- the order
+   *                   MPI_Cart_create / MPI_Cart_coords use (create_topology_mpi, :506-568);
+   *   OSGPU_TOPO_OLD  (1, "old"): x1 fastest (create_topology_old, :574-625);
+   *   OSGPU_TOPO_HOST (2): no assumption -- the neighbours are `neighbor` below, which the host copies
+   *                   from t_node_conf%neighbor(2,D) - 1 (mpi_cart_create may reorder ranks).
+   * For MPI / OLD the neighbours are derived from node_coords, and osgpu_init fails when `rank` is not
+   * the rank that topology gives those coordinates. */
+  int32_t topology;
+  int32_t neighbor[2][OSGPU_MAX_DIM]; /* [lower|upper][axis] NCCL rank, -1 none (OSGPU_TOPO_HOST) */
 } osgpu_config;
 #define OSGPU_PBC_ABSORB 0
 #define OSGPU_PBC_SPECULAR 1
+#define OSGPU_TOPO_MPI 0
+#define OSGPU_TOPO_OLD 1
+#define OSGPU_TOPO_HOST 2
 
 /* ---- library / topology helpers (no GPU needed) -------------------------------------- */
 const char *osgpu_version(void);
 const char *osgpu_last_error(void);
 int osgpu_device_count(void);
-/* cartesian rank <-> coords, x fastest; neighbour(2,D) of t_node_conf (os-nconf.f03:1101-1112):
- * neighbors[2*d+0] = lower, [2*d+1] = upper, -1 where there is none */
-int osgpu_cart_rank(int dim, const int32_t *dims, const int32_t *coords);
-int osgpu_cart_coords(int dim, const int32_t *dims, int rank, int32_t *coords);
-int osgpu_cart_neighbors(int dim, const int32_t *dims, const int32_t *periodic, int rank,
+/* cartesian rank <-> coords for topology OSGPU_TOPO_MPI (last axis fastest, MPI_Cart_create) or
+ * OSGPU_TOPO_OLD (x1 fastest); neighbour(2,D) of t_node_conf (os-nconf.f03:547-559, 596-625):
+ * neighbors[2*d+0] = lower, [2*d+1] = upper, -1 where there is none.  osgpu_cart_rank returns -1
+ * for OSGPU_TOPO_HOST (the mapping is the host's). */
+int osgpu_cart_rank(int topology, int dim, const int32_t *dims, const int32_t *coords);
+int osgpu_cart_coords(int topology, int dim, const int32_t *dims, int rank, int32_t *coords);
+int osgpu_cart_neighbors(int topology, int dim, const int32_t *dims, const int32_t *periodic, int rank,
                          int32_t *neighbors);
 /* guard-cell exchange ranges along `axis` (vdf/os-vdf-comm.f90:756-784, 866-894), cell indices
  * inclusive.  mode 0 = replace (E,B), 1 = add (J).  out = {send_lo0, send_lo1, send_up0, send_up1,
@@ -247,6 +262,10 @@ int osgpu_vadvance_deposit(int dim, int order, int real_bytes, int *ix, void *x,
                            int i0, int i1, double rqm, const void *efield, const void *bfield,
                            const int *emf_size, const int *emf_offset, void *j, const int *j_size,
                            const int *j_offset, const double *dx, double dt, double *ene);
+/* The stateless entry points keep the device state of the last call (grids, particle buffers,
+ * streams) per host thread and reuse it while dim/order/sizes/rqm are unchanged -- the reference
+ * calls its pusher once per thread chunk per step (spec/os-spec-vpush.f03:380-397).  This drops it. */
+void osgpu_vadvance_deposit_release(void);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,9 @@ struct SimBase {
 // page-locked memory instead of cudaMemcpy: a small copy queued on a copy engine waits behind whatever
 // multi-hundred-MB particle transfer is in flight there, and with uploads and downloads running on
 // both engines that serialised the two directions (measured: 218 ms/step instead of 157).
+__global__ void clamp_counts_kernel(int *cnt, int n, int cap) {
+  if ((int)threadIdx.x < n) cnt[threadIdx.x] = min(cnt[threadIdx.x], cap);
+}
 __global__ void ctl_copy_kernel(int *dst, const int *src, int nwords) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
@@ -120,13 +123,13 @@ template <typename T> struct Sim final : SimBase {
   };
   std::vector<Species> sp;
   cudaStream_t st_d2h = nullptr;  // device -> host copies of species_download_async
-  cudaEvent_t ev_dl;
+  cudaEvent_t ev_dl = nullptr;
   cudaStream_t st_h2d = nullptr;  // host -> device copies of species_upload_begin
   char *up_mem[2] = {nullptr, nullptr};  // two staging areas: one is sorted while the other fills
   size_t up_cap[2] = {0, 0};
   int up_next = 0;
   int up_owner[2] = {-1, -1};  // species whose begun upload occupies the area
-  cudaEvent_t ev_up_done[2], ev_up_free[2];
+  cudaEvent_t ev_up_done[2] = {nullptr, nullptr}, ev_up_free[2] = {nullptr, nullptr};
 
   int *d_err = nullptr;     // device error flags
   int *d_cnt = nullptr;     // small device scratch (send/recv counters)
@@ -176,8 +179,8 @@ template <typename T> struct Sim final : SimBase {
   T *xbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // field exchange: send lo/up, recv from up/lo
   size_t xbuf_elems = 0;
   uint32_t *pbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // particle exchange buffers
-  int pbuf_rec = 0;
-  cudaEvent_t ev[10];  // 0..5 phase boundaries, 6/7 whole call, 8/9 push kernel
+  int pbuf_rec = 0, precv_rec = 0;  // records the send / receive buffers hold
+  cudaEvent_t ev[10] = {};  // 0..5 phase boundaries, 6/7 whole call, 8/9 push kernel
   double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double slack = 0.25;
   int push_events = 0;
@@ -187,7 +190,7 @@ template <typename T> struct Sim final : SimBase {
   int sm_order[3] = {0, 0, 0};
   SmoothCoef<T> sm_coef[3];
   T *jtmp = nullptr;
-  cudaEvent_t ev_sm[2];
+  cudaEvent_t ev_sm[2] = {nullptr, nullptr};
   // field smoothing for the particles (t_emf%smooth_type = "stand"): e_part, b_part
   bool emf_smooth_on = false;
   int em_order[3] = {0, 0, 0};
@@ -227,6 +230,41 @@ template <typename T> struct Sim final : SimBase {
     if (c->dt > cour) {
       set_error("Yee stability condition violated: dt = %g > %g", c->dt, cour);
       return OSGPU_ERR_STABILITY;
+    }
+    // neighbours (t_node_conf%neighbor, os-nconf.f03:547-559): the host's own table, or derived from
+    // this rank's coordinates with the topology's rank order
+    int nr = 1;
+    for (int d = 0; d < dim; d++) nr *= std::max(1, (int)c->node_dims[d]);
+    if (nr != std::max(1, (int)c->nranks)) {
+      set_error("node_dims product %d != nranks %d", nr, c->nranks);
+      return OSGPU_ERR_INVALID;
+    }
+    for (int k = 0; k < 6; k++) neigh[k] = -1;
+    if (c->topology == OSGPU_TOPO_HOST) {
+      for (int d = 0; d < dim; d++)
+        for (int sd = 0; sd < 2; sd++) {
+          const int r = c->neighbor[sd][d];
+          if (r < -1 || r >= nr) { set_error("neighbor[%d][%d] = %d outside -1..%d", sd, d, r, nr - 1); return OSGPU_ERR_INVALID; }
+          neigh[2 * d + sd] = r;
+        }
+    } else if (c->topology == OSGPU_TOPO_MPI || c->topology == OSGPU_TOPO_OLD) {
+      int32_t dd[3] = {1, 1, 1};
+      for (int d = 0; d < dim; d++) {
+        dd[d] = std::max(1, (int)c->node_dims[d]);
+        if (c->node_coords[d] < 0 || c->node_coords[d] >= dd[d]) { set_error("node_coords[%d] = %d outside the node grid", d, c->node_coords[d]); return OSGPU_ERR_INVALID; }
+      }
+      const int me = osgpu_cart_rank(c->topology, dim, dd, c->node_coords);
+      if (me != c->rank) {
+        set_error("rank %d does not own node_coords (%d,%d,%d) under topology %d (that is rank %d): pass the host's "
+                  "neighbour table with OSGPU_TOPO_HOST", c->rank, c->node_coords[0], c->node_coords[1], c->node_coords[2], c->topology, me);
+        return OSGPU_ERR_INVALID;
+      }
+      int nb[6];
+      osgpu_cart_neighbors(c->topology, dim, dd, c->periodic, c->rank, nb);
+      for (int k = 0; k < 2 * dim; k++) neigh[k] = nb[k];
+    } else {
+      set_error("unknown topology %d", c->topology);
+      return OSGPU_ERR_INVALID;
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -294,16 +332,6 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     push_bps = push_blocks_per_sm<T>(dim, order);
 
-    // neighbours (t_node_conf%neighbor, os-nconf.f03:1101-1112)
-    int nb[6];
-    osgpu_cart_neighbors(dim, c->node_dims, c->periodic, c->rank, nb);
-    for (int k = 0; k < 6; k++) neigh[k] = (k < 2 * dim) ? nb[k] : -1;
-    int nr = 1;
-    for (int d = 0; d < dim; d++) nr *= std::max(1, (int)c->node_dims[d]);
-    if (nr != std::max(1, (int)c->nranks)) {
-      set_error("node_dims product %d != nranks %d", nr, c->nranks);
-      return OSGPU_ERR_INVALID;
-    }
     multi = nr > 1;
     if (multi) {
       if (!nccl_id) {
@@ -422,6 +450,7 @@ template <typename T> struct Sim final : SimBase {
         const size_t bytes = (size_t)rec * record_words<T>(dim) * 4;
         for (auto &b : pbuf) OSGPU_CUDA(cudaMalloc(&b, bytes));
         pbuf_rec = rec;
+        precv_rec = rec;
       }
     }
     s.created = true;
@@ -1066,7 +1095,9 @@ template <typename T> struct Sim final : SimBase {
   int do_relayout(Species &s, bool with_arrivals) {
     std::vector<int> cnt(tl.ntile), arr(tl.ntile, 0), off;
     OSGPU_TRY(ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile));
-    if (with_arrivals && s.movers_pending) OSGPU_TRY(ctl_read(arr.data(), s.tile_arr, sizeof(int) * tl.ntile));
+    // tile_arr was written by the movers_route that precedes every call with arrivals -- also on a rank
+    // that took part in the migration with an empty list of its own (movers_pending false)
+    if (with_arrivals) OSGPU_TRY(ctl_read(arr.data(), s.tile_arr, sizeof(int) * tl.ntile));
     OSGPU_TRY(ctl_sync());
     std::vector<int> need(tl.ntile);
     for (int t = 0; t < tl.ntile; t++) need[t] = cnt[t] + arr[t];
@@ -1093,14 +1124,28 @@ template <typename T> struct Sim final : SimBase {
       if (!slo && !sup) continue;
       OSGPU_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(int), st));
       OSGPU_TRY(movers_classify<T>(s.mv, g, d, slo, sup, pbuf[0], pbuf[1], d_cnt, pbuf_rec, d_err, st, &launches));
+      // The counts that travel are the record counts of the messages that follow: a sender whose list
+      // overflowed its buffer clamps here (and has ERRF_SEND_OVERFLOW set, reported after the
+      // exchange), so both ends always post legs of the same size and a capacity problem comes back
+      // as an error code on the rank that has it instead of a mismatched collective.
+      clamp_counts_kernel<<<1, 32, 0, st>>>(d_cnt, 2, pbuf_rec);
+      OSGPU_CUDA(cudaGetLastError());
+      launches += 1;
       // counts: mine to lower/upper -> theirs from upper/lower
       OSGPU_TRY(nccl.exchange(d_cnt + 0, sizeof(int), slo ? lo : -1, d_cnt + 1, sizeof(int), sup ? up : -1,
                               d_cnt + 2, sizeof(int), sup ? up : -1, d_cnt + 3, sizeof(int), slo ? lo : -1, st));
       OSGPU_TRY(ctl_read(h_pin + 4, d_cnt, 4 * sizeof(int)));
       OSGPU_TRY(ctl_sync());
-      const int n_to_lo = std::min(h_pin[4], pbuf_rec), n_to_up = std::min(h_pin[5], pbuf_rec);
+      const int n_to_lo = h_pin[4], n_to_up = h_pin[5];
       const int n_from_up = h_pin[6], n_from_lo = h_pin[7];
-      if (n_from_up > pbuf_rec || n_from_lo > pbuf_rec) { set_error("migration buffer too small"); return OSGPU_ERR_CAPACITY; }
+      const int n_in = std::max(n_from_up, n_from_lo);
+      if (n_in > precv_rec) {  // a neighbour with a larger species sends more than this rank ever would: grow
+        for (int k = 2; k < 4; k++) { if (pbuf[k]) cudaFree(pbuf[k]); pbuf[k] = nullptr; }
+        precv_rec = 0;
+        const size_t bytes = (size_t)n_in * rw * 4;
+        for (int k = 2; k < 4; k++) OSGPU_CUDA(cudaMalloc(&pbuf[k], bytes));
+        precv_rec = n_in;
+      }
       OSGPU_TRY(nccl.exchange(pbuf[0], (size_t)n_to_lo * rw * 4, slo ? lo : -1, pbuf[1], (size_t)n_to_up * rw * 4,
                               sup ? up : -1, pbuf[2], (size_t)n_from_up * rw * 4, sup ? up : -1, pbuf[3],
                               (size_t)n_from_lo * rw * 4, slo ? lo : -1, st));
@@ -1199,9 +1244,17 @@ template <typename T> struct Sim final : SimBase {
     if (h_ctl) cudaFreeHost(h_ctl);
     h_ctl = nullptr; ctl_cap = 0;
     nccl.destroy();
-    for (auto &e : ev) cudaEventDestroy(e);
-    if (st) cudaStreamDestroy(st);
-    st = nullptr;
+    auto drop_event = [](cudaEvent_t &e) { if (e) cudaEventDestroy(e); e = nullptr; };
+    auto drop_stream = [](cudaStream_t &q) { if (q) cudaStreamDestroy(q); q = nullptr; };
+    for (auto &e : ev) drop_event(e);
+    for (auto &e : ev_sm) drop_event(e);
+    for (auto &e : ev_up_done) drop_event(e);
+    for (auto &e : ev_up_free) drop_event(e);
+    drop_event(ev_dl);
+    drop_stream(st_d2h);
+    drop_stream(st_h2d);
+    drop_stream(st);
+    cudaGetLastError();  // (a failed init may leave a sticky-free error behind: do not hand it to the next call)
     return OSGPU_OK;
   }
 };
@@ -1227,27 +1280,40 @@ int osgpu_device_count(void) {
   return n;
 }
 
-int osgpu_cart_rank(int dim, const int32_t *dims, const int32_t *coords) {
+// OSGPU_TOPO_MPI: row-major, last axis fastest (MPI_Cart_create / mpi_cart_coords, os-nconf.f03:523-545);
+// OSGPU_TOPO_OLD: x1 fastest (create_topology_old, os-nconf.f03:586-592)
+int osgpu_cart_rank(int topology, int dim, const int32_t *dims, const int32_t *coords) {
+  if (topology != OSGPU_TOPO_MPI && topology != OSGPU_TOPO_OLD) return -1;
   int r = 0, mul = 1;
-  for (int d = 0; d < dim; d++) { r += mul * coords[d]; mul *= dims[d] > 0 ? dims[d] : 1; }
+  for (int k = 0; k < dim; k++) {
+    const int d = (topology == OSGPU_TOPO_OLD) ? k : dim - 1 - k;
+    r += mul * coords[d];
+    mul *= dims[d] > 0 ? dims[d] : 1;
+  }
   return r;
 }
-int osgpu_cart_coords(int dim, const int32_t *dims, int rank, int32_t *coords) {
-  for (int d = 0; d < dim; d++) { const int n = dims[d] > 0 ? dims[d] : 1; coords[d] = rank % n; rank /= n; }
+int osgpu_cart_coords(int topology, int dim, const int32_t *dims, int rank, int32_t *coords) {
+  if (topology != OSGPU_TOPO_MPI && topology != OSGPU_TOPO_OLD) { set_error("osgpu_cart_coords: the host owns the mapping of topology %d", topology); return OSGPU_ERR_INVALID; }
+  for (int k = 0; k < dim; k++) {
+    const int d = (topology == OSGPU_TOPO_OLD) ? k : dim - 1 - k;
+    const int n = dims[d] > 0 ? dims[d] : 1;
+    coords[d] = rank % n;
+    rank /= n;
+  }
   return OSGPU_OK;
 }
-int osgpu_cart_neighbors(int dim, const int32_t *dims, const int32_t *periodic, int rank, int32_t *nb) {
+int osgpu_cart_neighbors(int topology, int dim, const int32_t *dims, const int32_t *periodic, int rank, int32_t *nb) {
   int32_t c[3] = {0, 0, 0}, dd[3] = {1, 1, 1};
   for (int d = 0; d < dim; d++) dd[d] = dims[d] > 0 ? dims[d] : 1;
-  osgpu_cart_coords(dim, dd, rank, c);
+  if (osgpu_cart_coords(topology, dim, dd, rank, c) != OSGPU_OK) return OSGPU_ERR_INVALID;
   for (int d = 0; d < dim; d++) {
     for (int side = 0; side < 2; side++) {
       int32_t cc[3] = {c[0], c[1], c[2]};
       cc[d] += side ? 1 : -1;
       int r = -1;
       if (cc[d] < 0 || cc[d] >= dd[d]) {
-        if (periodic[d]) { cc[d] = (cc[d] + dd[d]) % dd[d]; r = osgpu_cart_rank(dim, dd, cc); }
-      } else r = osgpu_cart_rank(dim, dd, cc);
+        if (periodic[d]) { cc[d] = (cc[d] + dd[d]) % dd[d]; r = osgpu_cart_rank(topology, dim, dd, cc); }
+      } else r = osgpu_cart_rank(topology, dim, dd, cc);
       nb[2 * d + side] = r;
     }
   }
@@ -1373,6 +1439,19 @@ void *osgpu_host_alloc(size_t bytes) {
 void osgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ---- stateless pusher with the reference signature -------------------------------------------
+namespace {
+struct VadvCache {
+  osgpu_sim *h = nullptr;
+  osgpu_config cfg;
+  double rqm = 0;
+  long long np_max = 0;
+};
+thread_local VadvCache g_vadv;
+}  // namespace
+void osgpu_vadvance_deposit_release(void) {
+  if (g_vadv.h) osgpu_finalize(g_vadv.h);
+  g_vadv.h = nullptr;
+}
 int osgpu_vadvance_deposit(int dim, int order, int real_bytes, int *ix, void *x, void *u, void *q, int i0, int i1,
                            double rqm, const void *efield, const void *bfield, const int *emf_size,
                            const int *emf_offset, void *j, const int *j_size, const int *j_offset,
@@ -1400,20 +1479,32 @@ int osgpu_vadvance_deposit(int dim, int order, int real_bytes, int *ix, void *x,
   // this entry point does not advance fields
   c.dt = dt;
   c.nranks = 1; c.rank = 0; c.device = -1;
-  // stability is not this call's business: use a config that passes and restore dt below
-  osgpu_sim *h = nullptr;
+  // stability is not this call's business: use a config that passes and restore dt below.
+  // The reference calls its pusher once per thread chunk per step (spec/os-spec-vpush.f03:380-397): the
+  // handle (streams, events, grids, particle buffers) of the last call is kept per host thread and
+  // reused while the configuration is the same and the chunk fits; osgpu_vadvance_deposit_release()
+  // drops it.
   double cour = 0;
   for (int d = 0; d < dim; d++) cour += 1.0 / (dx[d] * dx[d]);
   cour = sqrt(1.0 / cour);
   osgpu_config ci = c;
   if (ci.dt > cour) ci.dt = cour;
-  int rc = osgpu_init(&h, &ci, nullptr);
-  if (rc != OSGPU_OK) return rc;
+  VadvCache &vc = g_vadv;
+  int rc = OSGPU_OK;
+  if (!(vc.h && memcmp(&vc.cfg, &ci, sizeof ci) == 0 && vc.rqm == rqm && np <= vc.np_max)) {
+    osgpu_vadvance_deposit_release();
+    rc = osgpu_init(&vc.h, &ci, nullptr);
+    if (rc != OSGPU_OK) { vc.h = nullptr; return rc; }
+    vc.cfg = ci;
+    vc.rqm = rqm;
+    vc.np_max = np + np / 8 + 1024;
+    if ((rc = osgpu_species_create(vc.h, 0, rqm, vc.np_max)) != OSGPU_OK) { osgpu_vadvance_deposit_release(); return rc; }
+  }
+  osgpu_sim *h = vc.h;
   const size_t es = (size_t)real_bytes;
   do {
     if (real_bytes == 4) static_cast<Sim<float> *>(h->impl)->cfg.dt = dt;
     else static_cast<Sim<double> *>(h->impl)->cfg.dt = dt;
-    if ((rc = osgpu_species_create(h, 0, rqm, np)) != OSGPU_OK) break;
     const size_t o = (size_t)(i0 - 1);
     if ((rc = osgpu_species_upload(h, 0, np, ix + dim * o, (char *)x + es * dim * o, (char *)u + es * 3 * o,
                                    (char *)q + es * o, nullptr)) != OSGPU_OK) break;
@@ -1435,7 +1526,7 @@ int osgpu_vadvance_deposit(int dim, int order, int real_bytes, int *ix, void *x,
     free(tmp);
     if (ene) *ene += e1;
   } while (0);
-  osgpu_finalize(h);
+  if (rc != OSGPU_OK) osgpu_vadvance_deposit_release();  // (the error text survives: finalize does not set one)
   return rc;
 }
 

@@ -30,7 +30,11 @@ class Config(C.Structure):
         ("node_dims", C.c_int32 * 3), ("node_coords", C.c_int32 * 3), ("periodic", C.c_int32 * 3),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32), ("smooth_order", C.c_int32),
         ("no_tags", C.c_int32), ("part_bc", (C.c_int32 * 3) * 2),
+        ("topology", C.c_int32), ("neighbor", (C.c_int32 * 3) * 2),
     ]
+
+
+TOPO_MPI, TOPO_OLD, TOPO_HOST = 0, 1, 2
 
 
 _lib = None
@@ -49,9 +53,9 @@ def load():
     vp, i32p, i64p, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
     L.osgpu_version.restype = C.c_char_p
     L.osgpu_last_error.restype = C.c_char_p
-    L.osgpu_cart_rank.argtypes = [C.c_int, i32p, i32p]
-    L.osgpu_cart_coords.argtypes = [C.c_int, i32p, C.c_int, i32p]
-    L.osgpu_cart_neighbors.argtypes = [C.c_int, i32p, i32p, C.c_int, i32p]
+    L.osgpu_cart_rank.argtypes = [C.c_int, C.c_int, i32p, i32p]
+    L.osgpu_cart_coords.argtypes = [C.c_int, C.c_int, i32p, C.c_int, i32p]
+    L.osgpu_cart_neighbors.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p]
     L.osgpu_exchange_ranges.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.osgpu_exchange_ranges_move.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.osgpu_min_gc.argtypes = [C.c_int, i32p]
@@ -143,5 +147,5 @@ EXPORTS = [
     "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
-    "osgpu_exchange_ranges_move",
+    "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -38,22 +38,32 @@ def min_gc_axes(dim, order, smooth_order=0, if_move=None):
 
 
 class NodeConf:
-    """t_node_conf (source/os-nconf.f03:45-107): cartesian rank layout, x fastest."""
+    """t_node_conf (source/os-nconf.f03:45-107).  topology = "mpi" (the reference's default: ranks laid
+    out as MPI_Cart_create does, last axis fastest, create_topology_mpi :506-568), "old" (x1 fastest,
+    create_topology_old :574-625) or "host": the caller supplies `neighbor` (and `coords`), the way a
+    Fortran host hands over t_node_conf%neighbor - 1 whatever mpi_cart_create decided."""
 
-    def __init__(self, dim, node_number=None, if_periodic=None, rank=0):
+    def __init__(self, dim, node_number=None, if_periodic=None, rank=0, topology="mpi", neighbor=None, coords=None):
         self.dim = dim
+        self.topology = {"mpi": _lib.TOPO_MPI, "old": _lib.TOPO_OLD, "host": _lib.TOPO_HOST}[topology]
         self.node_number = list(node_number) if node_number is not None else [1] * dim
         self.if_periodic = [bool(p) for p in (if_periodic if if_periodic is not None else [True] * dim)]
         self.rank = rank
         self.nranks = int(np.prod(self.node_number))
         L = _lib.load()
         dims = (C.c_int32 * 3)(*(self.node_number + [1] * (3 - dim)))
+        if self.topology == _lib.TOPO_HOST:
+            if neighbor is None or coords is None:
+                raise ValueError('topology "host" needs the neighbor table and the coordinates')
+            self.coords = [int(v) for v in coords]
+            self.neighbor = [[int(v) for v in pair] for pair in neighbor]
+            return
         co = (C.c_int32 * 3)()
-        L.osgpu_cart_coords(dim, dims, rank, co)
+        L.osgpu_cart_coords(self.topology, dim, dims, rank, co)
         self.coords = [int(co[d]) for d in range(dim)]
         nb = (C.c_int32 * 6)()
         per = (C.c_int32 * 3)(*([int(p) for p in self.if_periodic] + [0] * (3 - dim)))
-        L.osgpu_cart_neighbors(dim, dims, per, rank, nb)
+        L.osgpu_cart_neighbors(self.topology, dim, dims, per, rank, nb)
         # neighbor(2, D): [d][0] lower, [d][1] upper
         self.neighbor = [[int(nb[2 * d]), int(nb[2 * d + 1])] for d in range(dim)]
 
@@ -300,6 +310,9 @@ class Simulation:
             cfg.node_dims[d] = self.no_co.node_number[d]
             cfg.node_coords[d] = self.no_co.coords[d]
             cfg.periodic[d] = int(self.no_co.if_periodic[d])
+            for s in range(2):
+                cfg.neighbor[s][d] = self.no_co.neighbor[d][s]
+        cfg.topology = self.no_co.topology
         cfg.dt = self.dt
         cfg.rank, cfg.nranks, cfg.device, cfg.smooth_order = self.no_co.rank, self.no_co.nranks, device, smooth_order
         cfg.no_tags = 0 if add_tag else 1  # species{add_tag} (spec/os-spec-define.f03:431)

@@ -30,17 +30,75 @@ def test_library_exports_every_declared_symbol(built):
     assert set(lib.EXPORTS) <= set(names) | {"osgpu_sync", "osgpu_host_alloc", "osgpu_host_free"}
 
 
-def test_cartesian_topology_matches_mpi_cart_convention(built):
-    """x fastest rank order, periodic wrap, -1 on open edges (os-nconf.f03:506-568, 1101-1112)"""
+def test_cartesian_topology_old_is_x_fastest(built):
+    """create_topology_old (os-nconf.f03:574-625): x1 fastest, periodic wrap, -1 on open edges"""
     from osiris_b200.simulation import NodeConf
-    nc = NodeConf(3, [2, 2, 2], [True, True, True], rank=5)
+    nc = NodeConf(3, [2, 2, 2], [True, True, True], rank=5, topology="old")
     assert nc.coords == [1, 0, 1]
     assert nc.neighbor == [[4, 4], [7, 7], [1, 1]]
-    nc = NodeConf(2, [4, 2], [True, False], rank=3)
+    nc = NodeConf(2, [4, 2], [True, False], rank=3, topology="old")
     assert nc.coords == [3, 0]
     assert nc.neighbor == [[2, 0], [-1, 7]]
-    nc = NodeConf(3, [1, 1, 1], [True, True, True], rank=0)
+    nc = NodeConf(3, [1, 1, 1], [True, True, True], rank=0, topology="old")
     assert nc.neighbor == [[0, 0], [0, 0], [0, 0]]   # own periodic neighbour -> in-rank fold
+
+
+def test_cartesian_topology_mpi_is_row_major(built):
+    """create_topology_mpi (os-nconf.f03:506-568) takes coordinates and neighbours from MPI_Cart_coords /
+    MPI_Cart_shift of an MPI_Cart_create communicator: row-major, the LAST axis varies fastest
+    (rank = (c1 * n2 + c2) * n3 + c3), the reference's default topology."""
+    from osiris_b200 import lib
+    from osiris_b200.simulation import NodeConf
+    L = lib.load()
+    dims = (C.c_int32 * 3)(2, 3, 4)
+    seen = set()
+    for c1 in range(2):
+        for c2 in range(3):
+            for c3 in range(4):
+                co = (C.c_int32 * 3)(c1, c2, c3)
+                r = L.osgpu_cart_rank(lib.TOPO_MPI, 3, dims, co)
+                assert r == (c1 * 3 + c2) * 4 + c3
+                back = (C.c_int32 * 3)()
+                assert L.osgpu_cart_coords(lib.TOPO_MPI, 3, dims, r, back) == 0
+                assert list(back) == [c1, c2, c3]
+                seen.add(r)
+    assert seen == set(range(24))
+    nc = NodeConf(3, [2, 2, 2], [True, True, True], rank=5)        # default topology: "mpi"
+    assert nc.coords == [1, 0, 1]
+    assert nc.neighbor == [[1, 1], [7, 7], [4, 4]]                 # x neighbours are 4 ranks away, z neighbours 1
+    nc = NodeConf(2, [4, 2], [True, False], rank=3)
+    assert nc.coords == [1, 1]
+    assert nc.neighbor == [[1, 5], [2, -1]]
+    # the mapping of "host" is the host's: the helpers refuse to guess it
+    assert L.osgpu_cart_rank(lib.TOPO_HOST, 3, dims, (C.c_int32 * 3)(0, 0, 0)) == -1
+
+
+def test_init_rejects_a_rank_that_does_not_own_its_coordinates(built):
+    """a host that passes its cart-comm rank with coordinates of the other ordering must not silently
+    get wrong neighbours: osgpu_init fails before touching the device"""
+    from osiris_b200 import lib
+    L = lib.load()
+    cfg = lib.Config()
+    cfg.dim, cfg.order, cfg.real_bytes, cfg.nspecies = 2, 1, 4, 1
+    for d in range(2):
+        cfg.nx[d], cfg.dx[d] = 16, 1.0
+        cfg.gc_emf[0][d] = cfg.gc_jay[0][d] = 1
+        cfg.gc_emf[1][d] = cfg.gc_jay[1][d] = 2
+        cfg.periodic[d] = 1
+    cfg.node_dims[0], cfg.node_dims[1] = 4, 2
+    cfg.dt, cfg.nranks, cfg.device = 0.5, 8, -1
+    cfg.rank = 3
+    cfg.node_coords[0], cfg.node_coords[1] = 3, 0      # rank 3 of the x-fastest order ...
+    cfg.topology = lib.TOPO_MPI                           # ... declared as MPI order (where (3,0) is rank 6)
+    h = C.c_void_p()
+    rc = L.osgpu_init(C.byref(h), C.byref(cfg), None)
+    assert rc == -1 and b"does not own" in L.osgpu_last_error()   # (checked before any device call)
+    # the same coordinates with the order that matches, or with the host's own neighbour table, pass this check
+    cfg.topology = lib.TOPO_OLD
+    rc = L.osgpu_init(C.byref(h), C.byref(cfg), None)
+    assert b"does not own" not in L.osgpu_last_error()
+    if rc == 0:
+        L.osgpu_finalize(h)
 
 
 def test_exchange_ranges_follow_the_reference(built):

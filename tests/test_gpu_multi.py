@@ -132,7 +132,14 @@ def _window_run(sim, sp, dim, gnx, nxl, off, coords, node_dims, nsteps, dt, dx0,
     return nmoves
 
 
-def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_dir):
+def _keep_upper_half(part, off, gnx):
+    """plasma only in the upper half of the global box along x (the LWFA start: the window's trailing ranks
+    begin in vacuum and fill up one cell column per move)"""
+    m = (part["ix"][:, 0] + off[0]) > gnx[0] // 2
+    return {k: v[m] for k, v in part.items()}, m
+
+
+def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_dir, fill="full"):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from osiris_b200.loads import lattice_species
@@ -147,8 +154,13 @@ def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_
     off = [no_co.coords[d] * nxl[d] for d in range(dim)]
     ppc = 2 ** dim
     part = lattice_species(nxl, [2] * dim, dt_, uth=(0.2, 0.2, 0.2), global_nx=gnx, offset=off)
-    sp = sim.add_species("e", -1.0, 6 * len(part["q"]))
-    sp.upload(part["ix"], part["x"], part["p"], part["q"], tag=_global_tags(part, off, gnx, ppc))
+    tags = _global_tags(part, off, gnx, ppc)
+    cap = 6 * len(part["q"])
+    if fill == "upper":
+        part, m = _keep_upper_half(part, off, gnx)
+        tags = tags[m]
+    sp = sim.add_species("e", -1.0, cap)
+    sp.upload(part["ix"], part["x"], part["p"], part["q"], tag=tags)   # (an empty upload on the vacuum ranks)
     _window_run(sim, sp, dim, gnx, nxl, off, no_co.coords, node_dims, nsteps, 0.3, 0.5, dt_, int(np.prod(gnx)) * ppc)
     d = sp.fill_data(sort_by_tag=False)
     e, b = sim.emf.fill_data()
@@ -159,9 +171,10 @@ def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_
     sim.close()
 
 
-@pytest.mark.timeout(300)
-@pytest.mark.parametrize("dim,node_dims", [(2, [2, 1]), (3, [2, 1, 1]), (2, [2, 2])])
-def test_moving_window_across_ranks(built, tmp_path, dim, node_dims):
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("dim,node_dims,fill", [(2, [2, 1], "full"), (3, [2, 1, 1], "full"), (2, [2, 2], "full"),
+                                                (2, [2, 1], "upper"), (3, [2, 1, 1], "upper")])
+def test_moving_window_across_ranks(built, tmp_path, dim, node_dims, fill):
     """the window slides through a domain cut along x: the index shift sends one cell column of every
     rank to its lower neighbour, the lowest rank absorbs, the highest one injects.
 
@@ -178,15 +191,20 @@ def test_moving_window_across_ranks(built, tmp_path, dim, node_dims):
     prec, dt_ = "f32", np.float32
     gnx = [64, 32] if dim == 2 else [32, 16, 16]
     nsteps = 8
-    mp.spawn(_window_worker, args=(world, nccl_unique_id(), dim, prec, node_dims, gnx, nsteps, str(tmp_path)),
+    mp.spawn(_window_worker, args=(world, nccl_unique_id(), dim, prec, node_dims, gnx, nsteps, str(tmp_path), fill),
              nprocs=world, join=True)
     periodic = [False] + [True] * (dim - 1)
     bc = (["absorbing"] * dim, ["specular"] * dim)
     sim = Simulation(dim, 2, gnx, [0.5] * dim, 0.3, precision=prec, node_conf=NodeConf(dim, None, periodic, 0), part_bc=bc)
     ppc = 2 ** dim
     part = lattice_species(gnx, [2] * dim, dt_, uth=(0.2, 0.2, 0.2))
-    sp = sim.add_species("e", -1.0, 6 * len(part["q"]))
-    sp.upload(part["ix"], part["x"], part["p"], part["q"], tag=_global_tags(part, [0] * dim, gnx, ppc))
+    tags0 = _global_tags(part, [0] * dim, gnx, ppc)
+    cap = 6 * len(part["q"])
+    if fill == "upper":
+        part, m = _keep_upper_half(part, [0] * dim, gnx)
+        tags0 = tags0[m]
+    sp = sim.add_species("e", -1.0, cap)
+    sp.upload(part["ix"], part["x"], part["p"], part["q"], tag=tags0)
     nmoves = _window_run(sim, sp, dim, gnx, gnx, [0] * dim, [0] * dim, [1] * dim, nsteps, 0.3, 0.5, dt_, int(np.prod(gnx)) * ppc)
     assert nmoves >= 4
     ref = sp.fill_data()  # sorted by tag

@@ -110,12 +110,58 @@ template <int DIM, int ORDER, typename T> PIC_HD void tile_block(const T *p, T *
 }
 
 // ------------------------------------------------------------------------------------------
-// One particle, first half: interpolate E,B from the tile, Boris, move, trim.
-// x[], u[] and l[] are advanced in place; l[] may leave [0,T) by one cell.  x1[] is the new position
-// still in the old cell's frame (untrimmed), di[] the cell change, *vz (2D) the out-of-plane velocity;
-// returns u^2/(gamma+1) of the centred momentum.
-// Statement order follows ADVANCE_DEPOSIT_2D/3D (simd/os-spec-push-avx2.c:471-760, 1141-1472).
+// fp32 on the device: the six components are interpolated two at a time with the packed
+// fma.rn.f32x2 (SASS FFMA2, sm_100+): one instruction carries the same statement of two components
+// -- each half rounds exactly like the scalar fma it replaces, so the result is bit-identical to the
+// scalar nest below -- and halves the issue slots of the 39 (3D quadratic) fused multiply-adds per
+// component.  A weight that both halves share is a scalar operand (FFMA2 broadcasts a .F32 register),
+// a (plain, staggered) pair is kept as one register pair per axis and stencil point, and the
+// (staggered, plain) order is the same pair read with the halves swapped (operand modifier).
 // ------------------------------------------------------------------------------------------
+#ifndef OSGPU_FFMA2
+#define OSGPU_FFMA2 1
+#endif
+#if defined(__CUDA_ARCH__) && OSGPU_FFMA2
+// SEL: 0 both halves take the plain weight, 1 both the staggered one, 2 (plain, staggered), 3 (staggered, plain)
+template <int SEL> __device__ __forceinline__ float2 pair_weight(const float2 w) {
+  if constexpr (SEL == 0) return make_float2(w.x, w.x);
+  else if constexpr (SEL == 1) return make_float2(w.y, w.y);
+  else if constexpr (SEL == 2) return w;
+  else return make_float2(w.y, w.x);
+}
+// components A and B from their first stencil points pa, pb; wp[d][k] = (plain, staggered) weight of
+// point k along axis d.  Returns (A, B).
+template <int DIM, int ORDER, int SX, int SY, int SZ>
+__device__ __forceinline__ float2 interp_pair(const float *pa, const float *pb,
+                                              const float2 (*wp)[Stencil<ORDER>::NP]) {
+  using G = Tile<DIM, ORDER, float>;
+  constexpr int NP = G::NP;
+  constexpr int NZ = (DIM == 3) ? NP : 1;
+  float va[NP * NP * NZ], vb[NP * NP * NZ];
+  tile_block<DIM, ORDER, float>(pa, va);
+  tile_block<DIM, ORDER, float>(pb, vb);
+  float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+  for (int k3 = 0; k3 < NZ; k3++) {
+    float2 plane = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int k2 = 0; k2 < NP; k2++) {
+      float2 line = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int k1 = 0; k1 < NP; k1++)
+        line = __ffma2_rn(make_float2(va[k1 + NP * (k2 + NP * k3)], vb[k1 + NP * (k2 + NP * k3)]),
+                          pair_weight<SX>(wp[0][k1]), line);
+      plane = __ffma2_rn(line, pair_weight<SY>(wp[1][k2]), plane);
+    }
+    if constexpr (DIM == 3) acc = __ffma2_rn(plane, pair_weight<SZ>(wp[DIM - 1][k3]), acc);
+    else acc = plane;
+  }
+  return acc;
+}
+#endif
+
+// ------------------------------------------------------------------------------------------
+// One particle, first half: interpolate E,B from the tile, Boris, move, trim.
 template <int DIM, int ORDER, typename T>
 PIC_HD T push_move(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, T *x1, int *di, T *vz) {
   using G = Tile<DIM, ORDER, T>;
@@ -131,6 +177,34 @@ PIC_HD T push_move(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, T *x1
     bh[d] = l[d] + 1 - (neg ? 1 : 0);
   }
   T f[6];
+#if defined(__CUDA_ARCH__) && OSGPU_FFMA2
+  if constexpr (sizeof(T) == 4) {
+    float2 wp[DIM][NP];
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+      for (int k = 0; k < NP; k++) wp[d][k] = make_float2(w[d][k], wh[d][k]);
+    // first stencil point of a component with stagger flags (hx, hy, hz)
+    auto at = [&](int c, bool hx, bool hy, bool hz) -> const float * {
+      int o = (hx ? bh[0] : b0[0]) + G::EXP * (hy ? bh[1] : b0[1]);
+      if constexpr (DIM == 3) o += G::EXP * G::EY * (hz ? bh[DIM - 1] : b0[DIM - 1]);
+      return eb + c * G::ESTRIDE + o;
+    };
+    if constexpr (DIM == 2) {
+      // E1 (h,.) E2 (.,h) E3 (.,.)  B1 (.,h) B2 (h,.) B3 (h,h)
+      const float2 r0 = interp_pair<DIM, ORDER, 0, 2, 0>(at(2, false, false, false), at(1, false, true, false), wp);  // (E3, E2)
+      const float2 r1 = interp_pair<DIM, ORDER, 1, 0, 0>(at(0, true, false, false), at(4, true, false, false), wp);   // (E1, B2)
+      const float2 r2 = interp_pair<DIM, ORDER, 2, 1, 0>(at(3, false, true, false), at(5, true, true, false), wp);    // (B1, B3)
+      f[2] = r0.x; f[1] = r0.y; f[0] = r1.x; f[4] = r1.y; f[3] = r2.x; f[5] = r2.y;
+    } else {
+      // E1 (h,.,.) E2 (.,h,.) E3 (.,.,h)  B1 (.,h,h) B2 (h,.,h) B3 (h,h,.)
+      const float2 r0 = interp_pair<DIM, ORDER, 0, 2, 3>(at(2, false, false, true), at(1, false, true, false), wp);   // (E3, E2)
+      const float2 r1 = interp_pair<DIM, ORDER, 1, 2, 3>(at(4, true, false, true), at(5, true, true, false), wp);     // (B2, B3)
+      const float2 r2 = interp_pair<DIM, ORDER, 3, 2, 2>(at(0, true, false, false), at(3, false, true, true), wp);    // (E1, B1)
+      f[2] = r0.x; f[1] = r0.y; f[4] = r1.x; f[5] = r1.y; f[0] = r2.x; f[3] = r2.y;
+    }
+  } else
+#endif
   if constexpr (DIM == 2) {
     // staggering: E1 (h,.) E2 (.,h) E3 (.,.)  B1 (.,h) B2 (h,.) B3 (h,h)
 #pragma unroll

@@ -132,6 +132,10 @@ def _window_run(sim, sp, dim, gnx, nxl, off, coords, node_dims, nsteps, dt, dx0,
     return nmoves
 
 
+def _window_dt(dim):
+    return 0.3 if dim == 2 else 0.25  # inside the Yee limit dx / sqrt(dim) for dx = 0.5; the window (c = 1) moves a cell every 2 steps
+
+
 def _keep_upper_half(part, off, gnx):
     """plasma only in the upper half of the global box along x (the LWFA start: the window's trailing ranks
     begin in vacuum and fill up one cell column per move)"""
@@ -149,7 +153,8 @@ def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_
     periodic = [False] + [True] * (dim - 1)
     no_co = NodeConf(dim, node_dims, periodic, rank)
     bc = (["absorbing"] * dim, ["specular"] * dim)
-    sim = Simulation(dim, 2, nxl, [0.5] * dim, 0.3, precision=prec, node_conf=no_co, nccl_id=nccl_id, device=rank,
+    dt = _window_dt(dim)
+    sim = Simulation(dim, 2, nxl, [0.5] * dim, dt, precision=prec, node_conf=no_co, nccl_id=nccl_id, device=rank,
                      part_bc=bc)
     off = [no_co.coords[d] * nxl[d] for d in range(dim)]
     ppc = 2 ** dim
@@ -161,7 +166,7 @@ def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_
         tags = tags[m]
     sp = sim.add_species("e", -1.0, cap)
     sp.upload(part["ix"], part["x"], part["p"], part["q"], tag=tags)   # (an empty upload on the vacuum ranks)
-    _window_run(sim, sp, dim, gnx, nxl, off, no_co.coords, node_dims, nsteps, 0.3, 0.5, dt_, int(np.prod(gnx)) * ppc)
+    _window_run(sim, sp, dim, gnx, nxl, off, no_co.coords, node_dims, nsteps, dt, 0.5, dt_, int(np.prod(gnx)) * ppc)
     d = sp.fill_data(sort_by_tag=False)
     e, b = sim.emf.fill_data()
     gl = sim.gc_emf[0]
@@ -195,7 +200,8 @@ def test_moving_window_across_ranks(built, tmp_path, dim, node_dims, fill):
              nprocs=world, join=True)
     periodic = [False] + [True] * (dim - 1)
     bc = (["absorbing"] * dim, ["specular"] * dim)
-    sim = Simulation(dim, 2, gnx, [0.5] * dim, 0.3, precision=prec, node_conf=NodeConf(dim, None, periodic, 0), part_bc=bc)
+    dt = _window_dt(dim)
+    sim = Simulation(dim, 2, gnx, [0.5] * dim, dt, precision=prec, node_conf=NodeConf(dim, None, periodic, 0), part_bc=bc)
     ppc = 2 ** dim
     part = lattice_species(gnx, [2] * dim, dt_, uth=(0.2, 0.2, 0.2))
     tags0 = _global_tags(part, [0] * dim, gnx, ppc)
@@ -205,7 +211,7 @@ def test_moving_window_across_ranks(built, tmp_path, dim, node_dims, fill):
         tags0 = tags0[m]
     sp = sim.add_species("e", -1.0, cap)
     sp.upload(part["ix"], part["x"], part["p"], part["q"], tag=tags0)
-    nmoves = _window_run(sim, sp, dim, gnx, gnx, [0] * dim, [0] * dim, [1] * dim, nsteps, 0.3, 0.5, dt_, int(np.prod(gnx)) * ppc)
+    nmoves = _window_run(sim, sp, dim, gnx, gnx, [0] * dim, [0] * dim, [1] * dim, nsteps, dt, 0.5, dt_, int(np.prod(gnx)) * ppc)
     assert nmoves >= 4
     ref = sp.fill_data()  # sorted by tag
     e1, b1 = sim.emf.fill_data()

@@ -27,6 +27,28 @@ template <> struct Real<double> {
   static PIC_HD double sqrt(double a) { return ::sqrt(a); }
 };
 
+#if defined(__CUDA_ARCH__)
+// Two fp32 values that go through the same statements side by side (fma.rn.f32x2 / FFMA2 and its
+// add / multiply forms, sm_100+).  Each half rounds exactly like the scalar operation, so a template
+// written for T = float gives bit-identical halves when instantiated with T = F2.
+struct F2 {
+  float2 v;
+  __device__ __forceinline__ F2() {}
+  __device__ __forceinline__ F2(float a) : v(make_float2(a, a)) {}
+  __device__ __forceinline__ F2(double a) : v(make_float2((float)a, (float)a)) {}
+  __device__ __forceinline__ F2(float a, float b) : v(make_float2(a, b)) {}
+  __device__ __forceinline__ F2(float2 a) : v(a) {}
+};
+__device__ __forceinline__ F2 operator-(F2 a) { return F2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return F2(__fadd2_rn(a.v, b.v)); }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return F2(__fadd2_rn(a.v, (-b).v)); }
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) { return F2(__fmul2_rn(a.v, b.v)); }
+__device__ __forceinline__ F2 operator/(F2 a, F2 b) { return F2(a.v.x / b.v.x, a.v.y / b.v.y); }  // (spline constants only)
+template <> struct Real<F2> {
+  static __device__ __forceinline__ F2 fma(F2 a, F2 b, F2 c) { return F2(__ffma2_rn(a.v, b.v, c.v)); }
+};
+#endif
+
 template <typename T> PIC_HD T fmadd(T a, T b, T c) { return Real<T>::fma(a, b, c); }
 template <typename T> PIC_HD T fnmadd(T a, T b, T c) { return Real<T>::fma(-a, b, c); }
 template <typename T> PIC_HD T fmsub(T a, T b, T c) { return Real<T>::fma(a, b, -c); }

@@ -179,11 +179,17 @@ PIC_HD T push_move(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, T *x1
   T f[6];
 #if defined(__CUDA_ARCH__) && OSGPU_FFMA2
   if constexpr (sizeof(T) == 4) {
+    // (plain, staggered) weights of every axis from one packed evaluation of the spline: the halves are
+    // spline(x) = spline_t(1/2 - x, 1/2 + x) and splineh(x, h) = spline_t((1 - h) - x, h + x)
     float2 wp[DIM][NP];
 #pragma unroll
-    for (int d = 0; d < DIM; d++)
+    for (int d = 0; d < DIM; d++) {
+      const float hh = (x[d] < 0.0f) ? 1.0f : 0.0f;
+      F2 wk[NP];
+      spline_t<ORDER, F2>(F2(0.5f, 1.0f - hh) - F2(x[d]), F2(0.5f, hh) + F2(x[d]), wk);
 #pragma unroll
-      for (int k = 0; k < NP; k++) wp[d][k] = make_float2(w[d][k], wh[d][k]);
+      for (int k = 0; k < NP; k++) wp[d][k] = wk[k].v;
+    }
     // first stencil point of a component with stagger flags (hx, hy, hz)
     auto at = [&](int c, bool hx, bool hy, bool hz) -> const float * {
       int o = (hx ? bh[0] : b0[0]) + G::EXP * (hy ? bh[1] : b0[1]);

@@ -162,6 +162,9 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr bool TMA_J = sizeof(T) == 4;
   static constexpr int OFF_HEADS = OFF_HIST + G::NCELL * 4;
   static constexpr int SMEM_BYTES = OFF_HEADS + G::NCELL * 4;
+  // all instantiations but 3D fp64 are meant to run two CTAs per SM: 233472 bytes per SM, 1024 reserved
+  // per CTA, < 512 bytes of static shared variables in the kernel
+  static_assert((sizeof(T) == 8 && DIM == 3) || SMEM_BYTES + 512 + 1024 <= 233472 / 2, "two CTAs per SM");
   PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {
     return ((comp * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
   }

@@ -200,8 +200,12 @@ def main():
     dim, order = w["dim"], w["order"]
     nx = [max(16, int(round(n * args.scale))) for n in w["nx"]]
     es = 4 if args.prec == "f32" else 8
+    # the same dictionary on both arms (the driver compares them): everything that names the workload,
+    # nothing that was measured
     cfg_common = {"workload": args.workload, "dim": dim, "interpolation": order, "cells_per_gpu": nx,
                   "ppc": int(np.prod(w["ppc"])), "species": len(w["species"]), "precision": args.prec,
+                  "particles_per_gpu": int(np.prod(nx)) * int(np.prod(w["ppc"])) * len(w["species"]),
+                  "node_dims": node_dims(N, dim),
                   "cache": "inputs larger than L2 (particle buffers >> 126 MB)"}
 
     if args.impl == "reference":
@@ -213,7 +217,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": N, "steps": steps,
                 "warmup": warmup, "ms_per_step": 1e3 * info["seconds"] / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
-                "config": dict(cfg_common, sample=info["sample"]),
+                "config": cfg_common,
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                  "sample": info["sample"]},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -236,6 +240,7 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
     nd = node_dims(world, dim)
+    assert world == N or world == 1, f"--gpus {N} but WORLD_SIZE {world}"
     no_co = NodeConf(dim, nd, [True] * dim, rank)
     sim = Simulation(dim, order, nx, w["dx"], w["dt"], precision=args.prec, nspecies=len(w["species"]),
                      node_conf=no_co, nccl_id=nccl_id, device=local, add_tag=False)  # species{add_tag} default
@@ -278,6 +283,7 @@ def main():
         dev_ms, wall_ms = float(t[0]), float(t[1])
     else:
         wall_ms = wall * 1e3
+    assert npart == cfg_common["particles_per_gpu"]
     total_part = npart * world
     ms_per_step = dev_ms / steps
     value = total_part / (ms_per_step * 1e-3)
@@ -304,7 +310,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.prec, "data": "synthetic",
-            "config": dict(cfg_common, particles_per_gpu=npart, node_dims=nd, wall_ms_per_step=wall_ms / steps),
+            "config": cfg_common, "wall_ms_per_step": wall_ms / steps,
             "roofline": roof, "clocks": clocks, "gpu_launches": int(launches)}
 
     # ---- end to end through the C ABI with HOST buffers (N = 1) -----------------------------

@@ -188,6 +188,18 @@ int osgpu_particles_update_boundary(osgpu_sim *sim); /* spec/os-spec-boundary.f0
 int osgpu_current_zero(osgpu_sim *sim);
 int osgpu_species_push(osgpu_sim *sim, int sp_id);
 int osgpu_species_update_boundary(osgpu_sim *sim, int sp_id);
+/* replaces: accelerate_deposit (spec/os-spec-accel.f90:41-397), the pusher push_species selects while
+ * n(tstep) < udist%n_accelerate or < udist%n_q_incr (spec/os-species.f03:1499-1503; beam initialisation,
+ * decks/PWFAs).  The particles free-stream along x1 with the velocity of u_accel = u_frac * ufl1
+ * (use_particle_uacc: u_frac * their own p1), momenta stay, the current is deposited with q * q_frac
+ * and ADDED to J.  u_frac / q_frac are the host's grad_linear / grad_regressive values of the step
+ * (os-math.f90:743-775).  The species' energy is left as the plain sum q u^2/(gamma+1)
+ * (p_ene_recalc, spec/os-spec-define.f03:1040-1052).  Followed by osgpu_species_update_boundary. */
+int osgpu_species_accelerate(osgpu_sim *sim, int sp_id, double u_frac, double q_frac, double ufl1,
+                             int use_particle_uacc);
+/* energy sum of the species' last push (this%energy(1), spec/os-spec-define.f03:1030-1086; multiply by
+ * rqm * cell volume for get_energy) */
+int osgpu_species_energy(osgpu_sim *sim, int sp_id, double *ene);
 int osgpu_sort(osgpu_sim *sim);                      /* spec/os-species.f03:269-332           */
 int osgpu_current_update_boundary(osgpu_sim *sim); /* current/os-current-define.f03:683-727 */
 int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-482 (Yee)   */

@@ -27,10 +27,11 @@ _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 def build(force=False):
     """Compile the oracle (and, when /root/reference exists, oracle/_ref).  Building the checker
     is not using it."""
-    need = force or not all(
-        os.path.exists(os.path.join(HERE, f))
-        for f in ("libpic_oracle_f32.so", "libpic_oracle_f64.so", "libcpu_driver.so")
-    )
+    libs = [os.path.join(HERE, f) for f in ("libpic_oracle_f32.so", "libpic_oracle_f64.so", "libcpu_driver.so")]
+    srcs = [os.path.join(HERE, f) for f in ("pic_oracle.c", "cpu_driver.c")]
+    need = force or not all(os.path.exists(f) for f in libs)
+    if not need:  # a restatement edited after the last build
+        need = max(os.path.getmtime(f) for f in srcs) > min(os.path.getmtime(f) for f in libs)
     if os.path.isdir("/root/reference/source/simd") and not os.path.exists(
         os.path.join(REFDIR, "libref_avx2_f32.so")
     ):
@@ -56,6 +57,10 @@ class Oracle:
             C.c_int, C.c_int, _i32p, rp, rp, rp, C.c_int, C.c_int, self.creal, rp, rp,
             _i32p, _i32p, rp, _i32p, _i32p, _f64p, C.c_double, _f64p]
         L.oracle_advance_deposit.restype = None
+        L.oracle_accelerate_deposit.argtypes = [
+            C.c_int, C.c_int, _i32p, rp, rp, rp, C.c_long, self.creal, self.creal, self.creal, C.c_int,
+            rp, _i32p, _i32p, _f64p, C.c_double, _f64p]
+        L.oracle_accelerate_deposit.restype = None
         for fn in (L.oracle_dbdt,):
             fn.argtypes = [C.c_int, rp, rp, _i32p, _i32p, _i32p, _f64p, C.c_double]
             fn.restype = None
@@ -111,6 +116,15 @@ class Oracle:
         self.lib.oracle_advance_deposit(
             dim, order, ix, x, u, q, i0, n, rqm, e, b, esz, self._i(emf_gc[0]), j, jsz,
             self._i(j_gc[0]), np.ascontiguousarray(dx, np.float64), float(dt), ene)
+        return float(ene[0])
+
+    def accelerate_deposit(self, dim, order, ix, x, u, q, u_frac, q_frac, ufl1, use_particle_uacc, j, j_gc, dx, dt):
+        """accelerate_deposit (spec/os-spec-accel.f90): in place on ix, x, j; returns sum(q u^2/(gamma+1))."""
+        jsz = self._i(j.shape[::-1][1:1 + dim])
+        ene = np.zeros(1, np.float64)
+        self.lib.oracle_accelerate_deposit(dim, order, ix, x, u, q, q.shape[0], u_frac, q_frac, ufl1,
+                                           int(bool(use_particle_uacc)), j, jsz, self._i(j_gc[0]),
+                                           np.ascontiguousarray(dx, np.float64), float(dt), ene)
         return float(ene[0])
 
     def yee_advance(self, dim, e, b, j, nx, gc, dx, dt):

@@ -655,6 +655,64 @@ void oracle_advance_deposit(int dim, int order, int *ix, REAL *x, REAL *u, const
 }
 
 /* ------------------------------------------------------------------------------------
+ * oracle_accelerate_deposit: the beam-initialisation pusher, spec/os-spec-accel.f90:41-397
+ * (accelerate_deposit -> accelerate_deposit_2d :230-313, accelerate_deposit_3d :316-397).
+ * No fields: x1 advances by vdt_dx1 = u_accel dt/dx1 / sqrt(1 + u_accel^2) with
+ * u_accel = u_frac * ufl(1) (use_particle_uacc: u_frac * p(1)), the other coordinates and
+ * the momentum stay; the current is deposited with q * q_frac, dxi(2:3) = 0 and -- in 2D --
+ * rg = 0 (no out-of-plane current).  u_frac, q_frac, ufl1 arrive in particle precision
+ * like the Fortran locals.  The Fortran deposit (dep_current_2d/3d) is restated by the same
+ * splitter and stencil sums as the SIMD path (equal up to summation order).  *ene
+ * accumulates sum q u^2/(gamma+1) of the unchanged momenta (what get_energy recomputes after
+ * p_ene_recalc, spec/os-spec-define.f03:1040-1052).
+ * ---------------------------------------------------------------------------------- */
+void oracle_accelerate_deposit(int dim, int order, int *ix, REAL *x, const REAL *u, const REAL *q,
+                               long np, REAL u_frac, REAL q_frac, REAL ufl1, int use_particle_uacc,
+                               REAL *j, const int *j_size, const int *j_offset, const double *dx,
+                               double dt, double *ene) {
+  REAL jnorm[3];
+  for (int d = 0; d < dim; d++) jnorm[d] = (REAL)(dx[d] / dt / (dim == 2 ? 2 : 3));
+  const REAL dt_dx1 = (REAL)(dt / dx[0]);
+  const long jsy = 3L * j_size[0], jsz = jsy * j_size[1];
+  REAL *j11 = (REAL *)fld_at(j, j_size, j_offset, dim, 1, 1, 1);
+  double etot = 0.0;
+  for (long p = 0; p < np; p++) {
+    REAL *xp = x + dim * p;
+    const REAL *up = u + 3 * p;
+    int *ip = ix + dim * p;
+    const REAL u_accel = use_particle_uacc ? u_frac * up[0] : u_frac * ufl1;
+    const REAL vdt_dx1 = (u_accel * dt_dx1) / SQRT(R(1.0) + u_accel * u_accel);
+    const REAL x1 = xp[0] + vdt_dx1;
+    const int tr = ntrim(x1);
+    const REAL u2 = up[0] * up[0] + up[1] * up[1] + up[2] * up[2];
+    etot += (double)q[p] * (double)(u2 / (SQRT(u2 + R(1.0)) + R(1.0)));
+    if (dim == 2) {
+      vp_t v[3 + VECW];
+      memset(v, 0, sizeof v);
+      v[0].x0 = xp[0]; v[0].x1 = x1; v[0].y0 = xp[1]; v[0].y1 = xp[1];
+      v[0].q = q[p] * q_frac; v[0].vz = R(0.0);
+      v[0].ix = ip[0]; v[0].iy = ip[1];
+      int n = 1;
+      split2d(v, 0, &n, tr ? 1 : 0, tr, 0);
+      dep2d(order, j11, jsy, jnorm, v, n);
+    } else {
+      vp3_t v[4 + VECW];
+      memset(v, 0, sizeof v);
+      for (int d = 0; d < 3; d++) { v[0].p0[d] = xp[d]; v[0].p1[d] = xp[d]; v[0].i[d] = ip[d]; }
+      v[0].p1[0] = x1;
+      v[0].q = q[p] * q_frac;
+      int n = 1;
+      const int di[3] = {tr, 0, 0};
+      split3d(v, 0, &n, tr ? 1 : 0, di);
+      dep3d_group(order, j11, jsy, jsz, jnorm, v, n);
+    }
+    xp[0] = x1 - (REAL)tr;
+    ip[0] += tr;
+  }
+  *ene += etot;
+}
+
+/* ------------------------------------------------------------------------------------
  * Yee solver.  emf/solver/os-emf-solver-yee.f03:102-138 (dbdt_2d), :211-251 (dbdt_3d),
  * :287-326 (dedt_2d), :385-428 (dedt_3d), :542-568 (advance_yee).
  * Grids: f(3, S1, S2[, S3]), cell (1,1,1) at padded position gcl.

@@ -224,7 +224,10 @@ __device__ __forceinline__ void flush_stencil(const T *acc, T *pj) {
       }
 }
 
-template <int DIM, int ORDER, typename T>
+// ACCEL: the beam-initialisation pusher (accelerate_deposit, spec/os-spec-accel.f90) instead of
+// interpolation + Boris; its own instantiation, because as a run-time branch its live values cost the
+// standard path 5 % (profiles/r2_notes.md)
+template <int DIM, int ORDER, typename T, bool ACCEL>
 __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2)
     push_deposit_kernel(const __grid_constant__ TmaMaps maps, const PushArgs<T> a) {
   using G = Tile<DIM, ORDER, T>;
@@ -539,7 +542,14 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               seg[0].c[d] = l[d];
             }
             T vz = T(0);
-            const T en = push_move<DIM, ORDER, T>(x, u, l, eb, a.k, seg[0].p1, di, &vz);
+            T en, qd = q;  // qd: the charge the deposit sees
+            if constexpr (ACCEL) {  // beam initialisation: free streaming along x1, reduced charge
+              en = accel_move<DIM, T>(x, u, l, a.k.dt_dx[0], a.accel.per_particle ? a.accel.u_frac * u[0] : a.accel.u_frac * a.accel.ufl1,
+                                      seg[0].p1, di, &vz);
+              qd = q * a.accel.q_frac;
+            } else {
+              en = push_move<DIM, ORDER, T>(x, u, l, eb, a.k, seg[0].p1, di, &vz);
+            }
             ene_t = fmadd(q, en, ene_t);
             bool moved = false;
             int ncell = 0;
@@ -567,11 +577,12 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
 #pragma unroll
               for (int d = 0; d < DIM; d++) pb_[32 * (DIM + d)] = seg[0].p1[d];
               if (DIM == 2) pb_[32 * (DIM + 2)] = vz;
+              if constexpr (ACCEL) pb_[32 * (DIM + 3)] = qd;  // (the deposit reads the charge from the staged slot)
               cross |= !parked;
             } else {
               if (DIM == 2) seg[0].vz = vz;
               const int nseg = split_trajectory<DIM, T>(seg, di);
-              deposit_segments<DIM, ORDER, T>(seg, nseg, 0xfu, q, jt, a.k, atomic_add);
+              deposit_segments<DIM, ORDER, T>(seg, nseg, 0xfu, qd, jt, a.k, atomic_add);
             }
           }
           }  // !done
@@ -900,10 +911,10 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
   }
 }
 
-template <int DIM, int ORDER, typename T>
+template <int DIM, int ORDER, typename T, bool ACCEL>
 static int launch(const TmaMaps &maps, const PushArgs<T> &a, int nblocks, cudaStream_t st) {
   using P = Plan<DIM, ORDER, T>;
-  auto kern = push_deposit_kernel<DIM, ORDER, T>;
+  auto kern = push_deposit_kernel<DIM, ORDER, T, ACCEL>;
   static bool configured = false;
   const int smem = P::SMEM_BYTES;
   if (!configured) {
@@ -919,7 +930,7 @@ template <typename T>
 int launch_push_deposit(int dim, int order, const TmaMaps &maps, const PushArgs<T> &a, int nblocks,
                         cudaStream_t st) {
 #define CASE(D, O) \
-  if (dim == D && order == O) return launch<D, O, T>(maps, a, nblocks, st);
+  if (dim == D && order == O) return a.accel.on ? launch<D, O, T, true>(maps, a, nblocks, st) : launch<D, O, T, false>(maps, a, nblocks, st);
   CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 1) CASE(3, 2) CASE(3, 3) CASE(3, 4)
 #undef CASE
   set_error("unsupported dim/order %d/%d", dim, order);
@@ -950,7 +961,7 @@ template <typename T> int push_blocks_per_sm(int dim, int order) {
   int nb = 1;
 #define CASE(D, O)                                                                                   \
   if (dim == D && order == O) {                                                                      \
-    auto kern = push_deposit_kernel<D, O, T>;                                                        \
+    auto kern = push_deposit_kernel<D, O, T, false>;                                                 \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Plan<D, O, T>::SMEM_BYTES); \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NTHREADS, Plan<D, O, T>::SMEM_BYTES);    \
   }

@@ -22,6 +22,16 @@ template <typename T> struct Cols {
   long long *tag;
 };
 
+// accelerate_deposit (spec/os-spec-accel.f90:41-397), the pusher of the first n_accelerate / n_q_incr
+// steps of a beam species: no fields, the particle free-streams along x1 with the velocity of
+// u_accel = u_frac * ufl(1) (or u_frac * its own p1), momenta untouched, current deposited with q * q_frac
+template <typename T> struct Accel {
+  int on;             // 0: the standard pusher
+  int per_particle;   // udist%use_particle_uacc
+  T u_frac, q_frac;   // grad_linear / grad_regressive of the step (host side)
+  T ufl1;             // udist%ufl(1)
+};
+
 template <typename T> struct PushArgs {
   SpeciesView<T> spc;   // species buffer
   SpeciesView<T> scc;   // per-CTA scratch ranges: new state in the old order (cell = new packed cell)
@@ -38,6 +48,7 @@ template <typename T> struct PushArgs {
   Grid g;
   Tiling tl;
   pic::PushConst<T> k;
+  Accel<T> accel;
   double *ene;   // += sum(q * u^2/(gamma+1)) over the species
   int *errflag;
 };

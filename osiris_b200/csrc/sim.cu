@@ -57,7 +57,9 @@ struct SimBase {
   virtual int emf_advance() = 0;
   virtual int current_zero() = 0;
   virtual int species_push(int id) = 0;
+  virtual int species_accelerate(int id, double u_frac, double q_frac, double ufl1, int use_particle_uacc) = 0;
   virtual int species_update_boundary(int id) = 0;
+  virtual int species_energy(int id, double *ene) = 0;
   virtual int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) = 0;
   virtual int sync_all() = 0;
   virtual int move_window(const int *nmove) = 0;
@@ -989,6 +991,23 @@ template <typename T> struct Sim final : SimBase {
 
   // push_species for one species (spec/os-species.f03:1461-1520): its current is ADDED to J
   int species_push(int id) override {
+    Accel<T> none;
+    memset(&none, 0, sizeof none);
+    return species_push_impl(id, none);
+  }
+  // accelerate_deposit (spec/os-spec-accel.f90:41-121): what push_species runs instead of the pusher while
+  // n < n_accelerate or n < n_q_incr (spec/os-species.f03:1499-1503).  u_frac and q_frac are the host's
+  // grad_linear / grad_regressive values of the step, in particle precision like the reference's locals.
+  int species_accelerate(int id, double u_frac, double q_frac, double ufl1, int use_particle_uacc) override {
+    Accel<T> ac;
+    ac.on = 1;
+    ac.per_particle = use_particle_uacc ? 1 : 0;
+    ac.u_frac = (T)u_frac;
+    ac.q_frac = (T)q_frac;
+    ac.ufl1 = (T)ufl1;
+    return species_push_impl(id, ac);
+  }
+  int species_push_impl(int id, const Accel<T> &accel) {
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
     if (s.movers_pending) { set_error("species %d pushed twice without update_boundary", id); return OSGPU_ERR_INVALID; }
@@ -1019,6 +1038,7 @@ template <typename T> struct Sim final : SimBase {
       a.k.dt_dx[d] = (d < dim) ? (T)(dtp / cfg.dx[d]) : T(0);
       a.k.jnorm[d] = (d < dim) ? (T)(cfg.dx[d] / dtp / (dim == 2 ? 2 : 3)) : T(0);
     }
+    a.accel = accel;
     a.ene = s.d_ene;
     a.errflag = d_err;
     OSGPU_CUDA(cudaMemsetAsync(s.d_ene, 0, sizeof(double), st));
@@ -1029,6 +1049,14 @@ template <typename T> struct Sim final : SimBase {
     push_events++;
     launches += 1;
     s.movers_pending = true;
+    return OSGPU_OK;
+  }
+
+  // energy sum of the species' last push / accelerate call (this%energy, spec/os-spec-define.f03:1030-1086)
+  int species_energy(int id, double *ene) override {
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    OSGPU_CUDA(cudaMemcpyAsync(ene, sp[id].d_ene, sizeof(double), cudaMemcpyDeviceToHost, st));
+    OSGPU_CUDA(cudaStreamSynchronize(st));
     return OSGPU_OK;
   }
 
@@ -1427,6 +1455,15 @@ int osgpu_species_inject(osgpu_sim *h, int id, int64_t np, const int32_t *ix, co
 int osgpu_current_zero(osgpu_sim *h) { H_CHECK(h); return h->impl->current_zero(); }
 int osgpu_species_push(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_push(id); }
 int osgpu_species_update_boundary(osgpu_sim *h, int id) { H_CHECK(h); return h->impl->species_update_boundary(id); }
+int osgpu_species_accelerate(osgpu_sim *h, int id, double u_frac, double q_frac, double ufl1, int use_particle_uacc) {
+  H_CHECK(h);
+  return h->impl->species_accelerate(id, u_frac, q_frac, ufl1, use_particle_uacc);
+}
+int osgpu_species_energy(osgpu_sim *h, int id, double *ene) {
+  H_CHECK(h);
+  if (!ene) { osgpu::set_error("species_energy: null output"); return OSGPU_ERR_INVALID; }
+  return h->impl->species_energy(id, ene);
+}
 int osgpu_species_download_async(osgpu_sim *h, int id, int32_t *ix, void *x, void *p, void *q, int64_t *tag) {
   H_CHECK(h);
   return h->impl->species_download_async(id, ix, x, p, q, (long long *)tag);

@@ -273,6 +273,28 @@ PIC_HD T push_move(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, T *x1
   return ene;
 }
 
+// One particle of accelerate_deposit_{2d,3d} (spec/os-spec-accel.f90:230-397): x1 advances by
+// vdt_dx1 = u_accel dt/dx1 / sqrt(1 + u_accel^2), the other coordinates and the momentum stay; the
+// deposit sees no transverse motion (dxi(2:3) = 0, rg = 0 cancels the 2D out-of-plane current).
+// Returns u^2/(gamma+1) of the (unchanged) momentum, the term get_energy recomputes when the push left
+// p_ene_recalc (spec/os-spec-define.f03:1030-1086).
+template <int DIM, typename T>
+PIC_HD T accel_move(T *x, const T *u, int *l, T dt_dx1, T u_accel, T *x1, int *di, T *vz) {
+  const T vdt_dx1 = (u_accel * dt_dx1) / Real<T>::sqrt(T(1.0) + u_accel * u_accel);
+  x1[0] = x[0] + vdt_dx1;
+  di[0] = ntrim<T>(x1[0]);
+  x[0] = x1[0] - T(di[0]);
+  l[0] += di[0];
+#pragma unroll
+  for (int d = 1; d < DIM; d++) {
+    x1[d] = x[d];
+    di[d] = 0;
+  }
+  if constexpr (DIM == 2) *vz = T(0.0);
+  const T u2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+  return u2 / (Real<T>::sqrt(u2 + T(1.0)) + T(1.0));
+}
+
 // Split a trajectory (seg[0]: p0, untrimmed p1, cell c, 2D vz) at the cell faces it crosses
 // (simd/split-vec.h); di[] = ntrim(p1).  Returns the number of pieces.
 template <int DIM, typename T> PIC_HD int split_trajectory(Seg<DIM, T> *seg, const int *di) {
@@ -303,6 +325,7 @@ PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DI
 template <int DIM, int ORDER, typename T, class Out>
 PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Out out) {
   constexpr int NP = Stencil<ORDER>::NP;
+  {
   T s0[DIM][NP], s1[DIM][NP], wlv[DIM][NP];
 #pragma unroll
   for (int d = 0; d < DIM; d++) {
@@ -362,6 +385,7 @@ PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Ou
           if (k3 < NP - 1) out(2, k1, k2, k3, wlv[Z][k3], wp3[k2][k1]);
         }
   }
+}
 }
 
 // the (comp, k1, k2, k3) of every non-zero stencil entry, in segment_current's order

@@ -72,6 +72,8 @@ def load():
     L.osgpu_species_download_async.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     L.osgpu_species_push.argtypes = [vp, C.c_int]
     L.osgpu_species_update_boundary.argtypes = [vp, C.c_int]
+    L.osgpu_species_accelerate.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+    L.osgpu_species_energy.argtypes = [vp, C.c_int, dp]
     L.osgpu_current_zero.argtypes = [vp]
     L.osgpu_move_window.argtypes = [vp, vp]
     L.osgpu_species_inject.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
@@ -147,5 +149,6 @@ EXPORTS = [
     "osgpu_current_smooth", "osgpu_current_zero", "osgpu_species_push", "osgpu_species_update_boundary",
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
-    "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release",
+    "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release", "osgpu_species_accelerate",
+    "osgpu_species_energy",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -104,11 +104,50 @@ class Space:
         return list(self.move_num)
 
 
+def grad_linear(n, nmax):
+    """gradient_linear (os-math.f90:743-753): real(n) / real(nmax) in default (single) real"""
+    return float(np.float32(n) / np.float32(nmax))
+
+
+def grad_regressive(n, nmax):
+    """gradient_regressive (os-math.f90:761-775): st x / sqrt((st x)^2 + 1) scaled to reach 1 at n = nmax"""
+    st = 3.0
+    scaling = float(np.sqrt(np.float64(np.float32(st) ** 2 + np.float32(1.0)))) / st
+    x = float(np.float32(n) / np.float32(nmax))
+    return st * x / np.sqrt((st * x) ** 2 + 1.0) * scaling
+
+
+class UDist:
+    """The part of t_udist (spec/os-spec-udist.f03) the pusher dispatch reads: beam initialisation by
+    free streaming (n_accelerate) and by growing charge (n_q_incr); *_type is "linear" | "regressive"."""
+
+    def __init__(self, ufl=(0.0, 0.0, 0.0), n_accelerate=-1, n_accelerate_type="linear", n_q_incr=-1,
+                 n_q_incr_type="linear", use_particle_uacc=False):
+        self.ufl = [float(v) for v in ufl]
+        self.n_accelerate, self.n_accelerate_type = int(n_accelerate), n_accelerate_type
+        self.n_q_incr, self.n_q_incr_type = int(n_q_incr), n_q_incr_type
+        self.use_particle_uacc = bool(use_particle_uacc)
+
+    def use_accelerate(self, n):   # use_accelerate_udist (:1233-1243)
+        return n < self.n_accelerate
+
+    def use_q_incr(self, n):       # use_q_incr_udist (:1249-1259)
+        return n < self.n_q_incr
+
+    def fractions(self, n):
+        """(u_frac, q_frac) of step n as accelerate_deposit forms them (spec/os-spec-accel.f90:76-113)"""
+        g = {"linear": grad_linear, "regressive": grad_regressive}
+        u_frac = g[self.n_accelerate_type](n + 1, self.n_accelerate) if self.n_accelerate > 0 else 1.0
+        q_frac = g[self.n_q_incr_type](n + 1, self.n_q_incr) if self.n_q_incr > 0 else 1.0
+        return u_frac, q_frac
+
+
 class Species:
     """t_species (spec/os-spec-define.f03:327-549) device mirror."""
 
-    def __init__(self, sim, sp_id, name, rqm, num_par_max):
+    def __init__(self, sim, sp_id, name, rqm, num_par_max, udist=None):
         self.sim, self.sp_id, self.name, self.rqm = sim, sp_id, name, float(rqm)
+        self.udist = udist if udist is not None else UDist()
         check(sim._L.osgpu_species_create(sim._h, sp_id, float(rqm), int(num_par_max)))
 
     def upload(self, ix, x, p, q, tag=None):
@@ -159,10 +198,25 @@ class Species:
         check(self.sim._L.osgpu_species_inject(self.sim._h, self.sp_id, q.shape[0], ptr(ix), ptr(x), ptr(p), ptr(q),
                                                ptr(tag)))
 
-    def push(self):
+    def push(self, n=None):
         """push_species (spec/os-species.f03:1461-1520): advance + deposit this species alone; its
-        current is added to J (zero it first with sim.jay.zero())."""
+        current is added to J (zero it first with sim.jay.zero()).  n = n(tstep) selects the beam
+        initialisation pusher while n < n_accelerate or n < n_q_incr, as the reference's dispatch does."""
+        if n is not None and (self.udist.use_accelerate(n) or self.udist.use_q_incr(n)):
+            return self.accelerate(*self.udist.fractions(n))
         check(self.sim._L.osgpu_species_push(self.sim._h, self.sp_id))
+
+    def accelerate(self, u_frac, q_frac):
+        """accelerate_deposit (spec/os-spec-accel.f90:41-121)"""
+        check(self.sim._L.osgpu_species_accelerate(self.sim._h, self.sp_id, float(u_frac), float(q_frac),
+                                                   self.udist.ufl[0], int(self.udist.use_particle_uacc)))
+
+    @property
+    def energy(self):
+        """this%energy(1) of the last push (sum q u^2/(gamma+1); get_energy multiplies by rqm * cell volume)"""
+        e = C.c_double(0.0)
+        check(self.sim._L.osgpu_species_energy(self.sim._h, self.sp_id, C.byref(e)))
+        return e.value
 
     def update_boundary(self):
         """update_boundary_species (spec/os-spec-boundary.f03:1099-1232)"""
@@ -331,6 +385,7 @@ class Simulation:
         check(self._L.osgpu_init(C.byref(self._h), C.byref(cfg), idbuf))
         self.emf, self.jay, self.part = _Emf(self), _Current(self), _Particles(self)
         self.nspecies = nspecies
+        self.n = 0  # n(tstep): steps taken by iter()
         if smooth is not None:
             self.jay.set_smooth(smooth)
         if emf_smooth is not None:
@@ -348,16 +403,41 @@ class Simulation:
     def jay_shape(self):
         return self._shape(self.gc_jay)
 
-    def add_species(self, name, rqm, num_par_max):
-        sp = Species(self, len(self.part.species), name, rqm, num_par_max)
+    def add_species(self, name, rqm, num_par_max, udist=None):
+        sp = Species(self, len(self.part.species), name, rqm, num_par_max, udist)
         self.part.species.append(sp)
         return sp
 
     def iter(self, nsteps=1):
         """nsteps time steps entirely on the GPU; returns per-species kinetic energy sums of the
-        last step (iter_sim, os-simulation.f03:561-661)."""
+        last step (iter_sim, os-simulation.f03:561-661).  Steps in which a species still runs its beam
+        initialisation pusher (n < n_accelerate / n_q_incr) go phase by phase through the per-species
+        plug points, the others as one osgpu_step."""
         ene = np.zeros(max(1, self.nspecies), np.float64)
-        check(self._L.osgpu_step(self._h, int(nsteps), ene.ctypes.data_as(C.POINTER(C.c_double))))
+        done = 0
+        while done < nsteps:
+            n = self.n
+            if any(sp.udist.use_accelerate(n) or sp.udist.use_q_incr(n) for sp in self.part.species):
+                self.emf.update_boundary()
+                self.emf.update_particle_fld()
+                self.jay.zero()
+                for sp in self.part.species:
+                    sp.push(n)
+                for i, sp in enumerate(self.part.species):
+                    ene[i] = sp.energy
+                    sp.update_boundary()
+                self.jay.update_boundary()
+                self.jay.smooth()
+                self.emf.advance()
+                self.n += 1
+                done += 1
+                continue
+            last = max((max(sp.udist.n_accelerate, sp.udist.n_q_incr) for sp in self.part.species), default=0)
+            k = nsteps - done  # (no species switches pusher inside these steps: n >= every threshold)
+            assert n >= last
+            check(self._L.osgpu_step(self._h, int(k), ene.ctypes.data_as(C.POINTER(C.c_double))))
+            self.n += k
+            done += k
         return ene
 
     def move_window(self, nmove):

@@ -33,9 +33,10 @@ class OracleSim:
         self.e_part, self.b_part = self.e, self.b
         # particles use dt rounded to their precision (spec/os-spec-vpush.f03:374)
         self.dtp = float(self.dtype(self.dt))
+        self.n = 0  # n(tstep)
 
-    def add_species(self, rqm, ix, x, p, q, tag=None):
-        sp = dict(rqm=float(rqm), ix=np.ascontiguousarray(ix, np.int32).copy(),
+    def add_species(self, rqm, ix, x, p, q, tag=None, udist=None):
+        sp = dict(rqm=float(rqm), udist=udist, ix=np.ascontiguousarray(ix, np.int32).copy(),
                   x=np.ascontiguousarray(x, self.dtype).copy(), p=np.ascontiguousarray(p, self.dtype).copy(),
                   q=np.ascontiguousarray(q, self.dtype).copy())
         if tag is not None:
@@ -67,6 +68,13 @@ class OracleSim:
         for sp in self.species:
             if sp["q"].shape[0] == 0:
                 ene.append(0.0)
+                continue
+            ud = sp.get("udist")
+            if ud is not None and (ud.use_accelerate(self.n) or ud.use_q_incr(self.n)):  # push_species dispatch
+                u_frac, q_frac = ud.fractions(self.n)
+                ene.append(self.orc.accelerate_deposit(self.dim, self.order, sp["ix"], sp["x"], sp["p"], sp["q"],
+                                                       u_frac, q_frac, ud.ufl[0], ud.use_particle_uacc, self.j,
+                                                       self.gc_jay, self.dx, self.dtp))
                 continue
             ene.append(self.orc.advance_deposit(self.dim, self.order, sp["ix"], sp["x"], sp["p"], sp["q"],
                                                 sp["rqm"], self.e_part, self.b_part, self.gc_emf, self.j, self.gc_jay,
@@ -123,6 +131,7 @@ class OracleSim:
             self.current_update_boundary()
             self.current_smooth()
             self.emf_advance()
+            self.n += 1
         return ene
 
     def field_energy(self):

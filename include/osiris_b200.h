@@ -202,7 +202,18 @@ int osgpu_species_accelerate(osgpu_sim *sim, int sp_id, double u_frac, double q_
 int osgpu_species_energy(osgpu_sim *sim, int sp_id, double *ene);
 int osgpu_sort(osgpu_sim *sim);                      /* spec/os-species.f03:269-332           */
 int osgpu_current_update_boundary(osgpu_sim *sim); /* current/os-current-define.f03:683-727 */
-int osgpu_emf_advance(osgpu_sim *sim);             /* emf/os-emf-define.f03:467-482 (Yee)   */
+int osgpu_emf_advance(osgpu_sim *sim);
+/* replaces: the choice of the field solver, el_mag_fld{ solver = "yee" | "custom" } (new_solver_emf,
+ * emf/solver/os-emf-solver.f03:36-52), and for "custom" the stencil of t_emf_solver_fei
+ * (emf/solver/os-emf-solver-fei.f03): coef_e(1:n_coef) in dB/dt, coef_b(1:n_coef) in dE/dt, reals of the
+ * handle's precision, as read_input_fei leaves them for any emf_solver{ type } ("customized-coef" takes
+ * them from the deck, decks/PWFAs/beam-focus-3D).  Needs x1 guard cells (2 n_coef - 1, 2 n_coef) on E, B
+ * (min_gc_fei, :1995-2026); returns OSGPU_ERR_STABILITY when dt exceeds test_stability_fei's limit for
+ * these coefficients (:1370-1384).  Boundary tapering (taper_bnd) and the spectral current filter /
+ * correction (filter_current, correct_current: FFTW) are not built. */
+#define OSGPU_SOLVER_YEE 0
+#define OSGPU_SOLVER_CUSTOM 1
+int osgpu_emf_set_solver(osgpu_sim *sim, int type, int n_coef, const void *coef_e, const void *coef_b);             /* emf/os-emf-define.f03:467-482 (Yee)   */
 /* Current smoothing.  set_smooth takes what setup_smooth leaves in
  * t_smooth (vdf/os-vdf-smooth.f90:373-467): order[dim] and scoef[dim][2*max_order+1] in FIELD
  * precision (real(p_k_fld)), centre tap at index max_order; all orders 0 switches it off.

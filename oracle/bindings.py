@@ -68,6 +68,8 @@ class Oracle:
         L.oracle_dedt.restype = None
         L.oracle_yee_advance.argtypes = [C.c_int, rp, rp, rp, _i32p, _i32p, _i32p, _f64p, C.c_double]
         L.oracle_yee_advance.restype = None
+        L.oracle_fei_advance.argtypes = [C.c_int, rp, rp, rp, _i32p, _i32p, _i32p, _f64p, C.c_double, C.c_int, rp, rp]
+        L.oracle_fei_advance.restype = None
         L.oracle_update_periodic.argtypes = [C.c_int, rp, C.c_int, _i32p, _i32p, _i32p, C.c_int, C.c_int]
         L.oracle_update_periodic.restype = None
         L.oracle_particles_periodic.argtypes = [C.c_int, _i32p, C.c_long, _i32p]
@@ -130,6 +132,12 @@ class Oracle:
     def yee_advance(self, dim, e, b, j, nx, gc, dx, dt):
         self.lib.oracle_yee_advance(dim, e, b, j, self._i(nx), self._i(gc[0]), self._i(gc[1]),
                                     np.ascontiguousarray(dx, np.float64), float(dt))
+
+    def fei_advance(self, dim, e, b, j, nx, gc, dx, dt, coef_e, coef_b):
+        """advance_fei (emf/solver/os-emf-solver-fei.f03:2331-2363) with the given stencil coefficients"""
+        ce, cb = np.ascontiguousarray(coef_e, self.dtype), np.ascontiguousarray(coef_b, self.dtype)
+        self.lib.oracle_fei_advance(dim, e, b, j, self._i(nx), self._i(gc[0]), self._i(gc[1]),
+                                    np.ascontiguousarray(dx, np.float64), float(dt), len(ce), ce, cb)
 
     def dbdt(self, dim, b, e, nx, gc, dx, dt):
         self.lib.oracle_dbdt(dim, b, e, self._i(nx), self._i(gc[0]), self._i(gc[1]),

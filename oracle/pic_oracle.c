@@ -794,6 +794,99 @@ void oracle_yee_advance(int dim, REAL *e, REAL *b, const REAL *jay, const int *n
 }
 
 /* ------------------------------------------------------------------------------------
+ * Customized-stencil ("Fei") solver, emf/solver/os-emf-solver-fei.f03: dbdt_2d_fei :108-251,
+ * dedt_2d_fei :253-404, dbdt_3d_fei :406-565, dedt_3d_fei :567-730, advance_fei :2331-2363;
+ * no boundary tapering, no current filter.  coef_e(1:n) enters dB/dt, coef_b(1:n) dE/dt.
+ * ---------------------------------------------------------------------------------- */
+void oracle_fei_dbdt(int dim, REAL *b, const REAL *e, const int *nx, const int *gcl, const int *gcu,
+                     const double *dx, double dt, int n, const REAL *coef_e) {
+  const long S1 = nx[0] + gcl[0] + gcu[0], S2 = nx[1] + gcl[1] + gcu[1];
+  const REAL dtdx1 = (REAL)(dt / dx[0]), dtdx2 = (REAL)(dt / dx[1]);
+  const int lb = 1 - n, ub = nx[0] + n;
+  if (dim == 2) {
+    for (int i2 = 0; i2 <= nx[1] + 1; i2++)
+      for (int i1 = lb; i1 <= ub; i1++) {
+        REAL tmp;
+        F2(b, 0, i1, i2) = F2(b, 0, i1, i2) - dtdx2 * (F2(e, 2, i1, i2 + 1) - F2(e, 2, i1, i2));
+        tmp = R(0.0);
+        for (int j = 1; j <= n; j++) tmp = tmp + coef_e[j - 1] * (F2(e, 2, i1 + j, i2) - F2(e, 2, i1 - j + 1, i2));
+        F2(b, 1, i1, i2) = F2(b, 1, i1, i2) + dtdx1 * tmp;
+        tmp = R(0.0);
+        for (int j = 1; j <= n; j++) tmp = tmp + coef_e[j - 1] * (F2(e, 1, i1 + j, i2) - F2(e, 1, i1 - j + 1, i2));
+        F2(b, 2, i1, i2) = F2(b, 2, i1, i2) - dtdx1 * tmp + dtdx2 * (F2(e, 0, i1, i2 + 1) - F2(e, 0, i1, i2));
+      }
+  } else {
+    const REAL dtdx3 = (REAL)(dt / dx[2]);
+    for (int i3 = 0; i3 <= nx[2] + 1; i3++)
+      for (int i2 = 0; i2 <= nx[1] + 1; i2++)
+        for (int i1 = lb; i1 <= ub; i1++) {
+          REAL tmp;
+          F3(b, 0, i1, i2, i3) = F3(b, 0, i1, i2, i3) - dtdx2 * (F3(e, 2, i1, i2 + 1, i3) - F3(e, 2, i1, i2, i3)) +
+                                 dtdx3 * (F3(e, 1, i1, i2, i3 + 1) - F3(e, 1, i1, i2, i3));
+          tmp = R(0.0);
+          for (int j = 1; j <= n; j++)
+            tmp = tmp + coef_e[j - 1] * (F3(e, 2, i1 + j, i2, i3) - F3(e, 2, i1 - j + 1, i2, i3));
+          F3(b, 1, i1, i2, i3) = F3(b, 1, i1, i2, i3) + dtdx1 * tmp -
+                                 dtdx3 * (F3(e, 0, i1, i2, i3 + 1) - F3(e, 0, i1, i2, i3));
+          tmp = R(0.0);
+          for (int j = 1; j <= n; j++)
+            tmp = tmp + coef_e[j - 1] * (F3(e, 1, i1 + j, i2, i3) - F3(e, 1, i1 - j + 1, i2, i3));
+          F3(b, 2, i1, i2, i3) = F3(b, 2, i1, i2, i3) - dtdx1 * tmp +
+                                 dtdx2 * (F3(e, 0, i1, i2 + 1, i3) - F3(e, 0, i1, i2, i3));
+        }
+  }
+}
+
+void oracle_fei_dedt(int dim, REAL *e, const REAL *b, const REAL *jay, const int *nx, const int *gcl,
+                     const int *gcu, const double *dx, double dt, int n, const REAL *coef_b) {
+  const long S1 = nx[0] + gcl[0] + gcu[0], S2 = nx[1] + gcl[1] + gcu[1];
+  const REAL dtdx1 = (REAL)(dt / dx[0]), dtdx2 = (REAL)(dt / dx[1]), dtif = (REAL)dt;
+  const int lb = 2 - n, ub = nx[0] + n;
+  if (dim == 2) {
+    for (int i2 = 1; i2 <= nx[1] + 1; i2++)
+      for (int i1 = lb; i1 <= ub; i1++) {
+        REAL tmp;
+        F2(e, 0, i1, i2) = F2(e, 0, i1, i2) - dtif * F2(jay, 0, i1, i2) + dtdx2 * (F2(b, 2, i1, i2) - F2(b, 2, i1, i2 - 1));
+        tmp = R(0.0);
+        for (int j = 1; j <= n; j++) tmp = tmp + coef_b[j - 1] * (F2(b, 2, i1 + j - 1, i2) - F2(b, 2, i1 - j, i2));
+        F2(e, 1, i1, i2) = F2(e, 1, i1, i2) - dtif * F2(jay, 1, i1, i2) - dtdx1 * tmp;
+        tmp = R(0.0);
+        for (int j = 1; j <= n; j++) tmp = tmp + coef_b[j - 1] * (F2(b, 1, i1 + j - 1, i2) - F2(b, 1, i1 - j, i2));
+        F2(e, 2, i1, i2) = F2(e, 2, i1, i2) - dtif * F2(jay, 2, i1, i2) - dtdx2 * (F2(b, 0, i1, i2) - F2(b, 0, i1, i2 - 1)) +
+                           dtdx1 * tmp;
+      }
+  } else {
+    const REAL dtdx3 = (REAL)(dt / dx[2]);
+    for (int i3 = 1; i3 <= nx[2] + 1; i3++)
+      for (int i2 = 1; i2 <= nx[1] + 1; i2++)
+        for (int i1 = lb; i1 <= ub; i1++) {
+          REAL tmp;
+          F3(e, 0, i1, i2, i3) = F3(e, 0, i1, i2, i3) - dtif * F3(jay, 0, i1, i2, i3) +
+                                 dtdx2 * (F3(b, 2, i1, i2, i3) - F3(b, 2, i1, i2 - 1, i3)) -
+                                 dtdx3 * (F3(b, 1, i1, i2, i3) - F3(b, 1, i1, i2, i3 - 1));
+          tmp = R(0.0);
+          for (int j = 1; j <= n; j++)
+            tmp = tmp + coef_b[j - 1] * (F3(b, 2, i1 + j - 1, i2, i3) - F3(b, 2, i1 - j, i2, i3));
+          F3(e, 1, i1, i2, i3) = F3(e, 1, i1, i2, i3) - dtif * F3(jay, 1, i1, i2, i3) +
+                                 dtdx3 * (F3(b, 0, i1, i2, i3) - F3(b, 0, i1, i2, i3 - 1)) - dtdx1 * tmp;
+          tmp = R(0.0);
+          for (int j = 1; j <= n; j++)
+            tmp = tmp + coef_b[j - 1] * (F3(b, 1, i1 + j - 1, i2, i3) - F3(b, 1, i1 - j, i2, i3));
+          F3(e, 2, i1, i2, i3) = F3(e, 2, i1, i2, i3) - dtif * F3(jay, 2, i1, i2, i3) -
+                                 dtdx2 * (F3(b, 0, i1, i2, i3) - F3(b, 0, i1, i2 - 1, i3)) + dtdx1 * tmp;
+        }
+  }
+}
+
+void oracle_fei_advance(int dim, REAL *e, REAL *b, const REAL *jay, const int *nx, const int *gcl,
+                        const int *gcu, const double *dx, double dt, int n, const REAL *coef_e,
+                        const REAL *coef_b) {
+  oracle_fei_dbdt(dim, b, e, nx, gcl, gcu, dx, dt / 2.0, n, coef_e);
+  oracle_fei_dedt(dim, e, b, jay, nx, gcl, gcu, dx, dt, n, coef_b);
+  oracle_fei_dbdt(dim, b, e, nx, gcl, gcu, dx, dt / 2.0, n, coef_e);
+}
+
+/* ------------------------------------------------------------------------------------
  * Single-rank periodic guard-cell update along one axis.
  * vdf/os-vdf-comm.f90:142-326 (update_periodic_vdf).  mode 0 = replace, 1 = add.
  * ---------------------------------------------------------------------------------- */

@@ -98,6 +98,95 @@ template int yee_advance<double>(const Grid &, Field3<double>, Field3<double>, F
                                  const double *, double, cudaStream_t, long long *);
 
 // ---------------------------------------------------------------------------------------------
+// Customized-stencil solver (dbdt_2d/3d_fei, dedt_2d/3d_fei, advance_fei: emf/solver/
+// os-emf-solver-fei.f03:108-251, 253-404, 406-565, 567-730, 2331-2363), without boundary tapering and
+// current filtering.  B over x1 cells 1-n .. nx+n, E over 2-n .. nx+n (the guard cells are advanced
+// too: the stencil of the next half step reaches into them), the other axes as Yee.  The stencil sum
+// is formed like the reference: tmp = 0, tmp = tmp + coef(j) * (f(i+..) - f(i-..)), j = 1..n.
+// ---------------------------------------------------------------------------------------------
+template <int DIM, typename T>
+__global__ void __launch_bounds__(128)
+    fei_b_kernel(Field3<T> b, Field3<const T> e, Grid g, T dtdx1, T dtdx2, T dtdx3, SolverCoef<T> sc) {
+  const int n = sc.n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 1 - n;  // cell index 1-n .. nx+n
+  const int j = blockIdx.y, k = blockIdx.z;
+  if (i > g.nx[0] + n) return;
+  const long long sy = g.P0, sz = (long long)g.P0 * g.S[1];
+  const long long c = g.at(i - 1 + g.gl[0], j - 1 + g.gl[1], (DIM == 3) ? k - 1 + g.gl[2] : 0);
+  T t3 = T(0), t2 = T(0);  // stencil sums of E3 (for B2) and E2 (for B3)
+  for (int m = 1; m <= n; m++) {
+    t3 = t3 + sc.ce[m - 1] * (e.c[2][c + m] - e.c[2][c - m + 1]);
+    t2 = t2 + sc.ce[m - 1] * (e.c[1][c + m] - e.c[1][c - m + 1]);
+  }
+  const T e1 = e.c[0][c], e2 = e.c[1][c], e3 = e.c[2][c];
+  if (DIM == 2) {
+    b.c[0][c] = b.c[0][c] - dtdx2 * (e.c[2][c + sy] - e3);
+    b.c[1][c] = b.c[1][c] + dtdx1 * t3;
+    b.c[2][c] = b.c[2][c] - dtdx1 * t2 + dtdx2 * (e.c[0][c + sy] - e1);
+  } else {
+    b.c[0][c] = b.c[0][c] - dtdx2 * (e.c[2][c + sy] - e3) + dtdx3 * (e.c[1][c + sz] - e2);
+    b.c[1][c] = b.c[1][c] + dtdx1 * t3 - dtdx3 * (e.c[0][c + sz] - e1);
+    b.c[2][c] = b.c[2][c] - dtdx1 * t2 + dtdx2 * (e.c[0][c + sy] - e1);
+  }
+}
+
+template <int DIM, typename T>
+__global__ void __launch_bounds__(128)
+    fei_e_kernel(Field3<T> e, Field3<const T> b, Field3<const T> jay, Grid g, T dtdx1, T dtdx2, T dtdx3, T dtif,
+                 SolverCoef<T> sc) {
+  const int n = sc.n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x + 2 - n;  // cell index 2-n .. nx+n
+  const int j = blockIdx.y + 1, k = blockIdx.z + 1;
+  if (i > g.nx[0] + n) return;
+  const long long sy = g.P0, sz = (long long)g.P0 * g.S[1];
+  const long long c = g.at(i - 1 + g.gl[0], j - 1 + g.gl[1], (DIM == 3) ? k - 1 + g.gl[2] : 0);
+  T t3 = T(0), t2 = T(0);  // stencil sums of B3 (for E2) and B2 (for E3)
+  for (int m = 1; m <= n; m++) {
+    t3 = t3 + sc.cb[m - 1] * (b.c[2][c + m - 1] - b.c[2][c - m]);
+    t2 = t2 + sc.cb[m - 1] * (b.c[1][c + m - 1] - b.c[1][c - m]);
+  }
+  const T b1 = b.c[0][c], b2 = b.c[1][c], b3 = b.c[2][c];
+  if (DIM == 2) {
+    e.c[0][c] = e.c[0][c] - dtif * jay.c[0][c] + dtdx2 * (b3 - b.c[2][c - sy]);
+    e.c[1][c] = e.c[1][c] - dtif * jay.c[1][c] - dtdx1 * t3;
+    e.c[2][c] = e.c[2][c] - dtif * jay.c[2][c] - dtdx2 * (b1 - b.c[0][c - sy]) + dtdx1 * t2;
+  } else {
+    e.c[0][c] = e.c[0][c] - dtif * jay.c[0][c] + dtdx2 * (b3 - b.c[2][c - sy]) - dtdx3 * (b2 - b.c[1][c - sz]);
+    e.c[1][c] = e.c[1][c] - dtif * jay.c[1][c] + dtdx3 * (b1 - b.c[0][c - sz]) - dtdx1 * t3;
+    e.c[2][c] = e.c[2][c] - dtif * jay.c[2][c] - dtdx2 * (b1 - b.c[0][c - sy]) + dtdx1 * t2;
+  }
+}
+
+template <typename T>
+int fei_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+                const SolverCoef<T> &sc, cudaStream_t st, long long *launches) {
+  const double dtb = dt / 2.0;
+  const T hb1 = (T)(dtb / dx[0]), hb2 = (T)(dtb / dx[1]), hb3 = (g.dim == 3) ? (T)(dtb / dx[2]) : T(0);
+  const T he1 = (T)(dt / dx[0]), he2 = (T)(dt / dx[1]), he3 = (g.dim == 3) ? (T)(dt / dx[2]) : T(0);
+  const T dtif = (T)dt;
+  Field3<const T> ce{{e.c[0], e.c[1], e.c[2]}}, cb{{b.c[0], b.c[1], b.c[2]}}, cj{{jay.c[0], jay.c[1], jay.c[2]}};
+  const dim3 blk(128);
+  const dim3 gb((g.nx[0] + 2 * sc.n + 127) / 128, g.nx[1] + 2, g.dim == 3 ? g.nx[2] + 2 : 1);
+  const dim3 ge((g.nx[0] + 2 * sc.n - 1 + 127) / 128, g.nx[1] + 1, g.dim == 3 ? g.nx[2] + 1 : 1);
+  if (g.dim == 2) {
+    fei_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+    fei_e_kernel<2, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif, sc);
+    fei_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+  } else {
+    fei_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+    fei_e_kernel<3, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif, sc);
+    fei_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+  }
+  *launches += 3;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int fei_advance<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>, const double *, double,
+                                const SolverCoef<float> &, cudaStream_t, long long *);
+template int fei_advance<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>, const double *, double,
+                                 const SolverCoef<double> &, cudaStream_t, long long *);
+
+// ---------------------------------------------------------------------------------------------
 // Current smoothing: one pass of the separable digital filter along `axis`, src -> dst
 // (filter_2d / filter_3d, source/vdf/os-vdf-smooth.f90:639-828, 834-1105).  The reference filters
 // in place with a sliding window of unfiltered values; out of place that is dst = filter(src).

@@ -7,6 +7,16 @@ namespace osgpu {
 template <typename T>
 int yee_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
                 cudaStream_t st, long long *launches);
+// customized-stencil ("Fei") solver, emf/solver/os-emf-solver-fei.f03: the x1 derivative of the Yee
+// curl becomes an antisymmetric n_coef-point stencil with coef_e (in dB/dt) and coef_b (in dE/dt)
+constexpr int SOLVER_MAX_NCOEF = 64;
+template <typename T> struct SolverCoef {
+  int n;
+  T ce[SOLVER_MAX_NCOEF], cb[SOLVER_MAX_NCOEF];
+};
+template <typename T>
+int fei_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+                const SolverCoef<T> &sc, cudaStream_t st, long long *launches);
 // mode 0 = replace, 1 = add; comps = 3 (J) or 6 (E,B) component planes
 template <typename T>
 int periodic_update(const Grid &g, T *const *comps, int ncomp, int axis, int mode, cudaStream_t st,

@@ -55,6 +55,7 @@ struct SimBase {
   virtual int sort() = 0;
   virtual int current_update_boundary() = 0;
   virtual int emf_advance() = 0;
+  virtual int emf_set_solver(int type, int n_coef, const void *coef_e, const void *coef_b) = 0;
   virtual int current_zero() = 0;
   virtual int species_push(int id) = 0;
   virtual int species_accelerate(int id, double u_frac, double q_frac, double ufl1, int use_particle_uacc) = 0;
@@ -889,7 +890,48 @@ template <typename T> struct Sim final : SimBase {
     T *comps[3] = {J.c[0], J.c[1], J.c[2]};
     return update_guards(comps, 3, 1);
   }
-  int emf_advance() override { return yee_advance<T>(g, E, B, J, cfg.dx, cfg.dt, st, &launches); }
+  int emf_advance() override {
+    if (solver_custom) return fei_advance<T>(g, E, B, J, cfg.dx, cfg.dt, solver_coef, st, &launches);
+    return yee_advance<T>(g, E, B, J, cfg.dx, cfg.dt, st, &launches);
+  }
+  // el_mag_fld{ solver = "yee" | "custom" } (new_solver_emf, emf/solver/os-emf-solver.f03:36-52).  The
+  // customized solver takes the stencil coefficients read_input_fei ends up with, whatever their
+  // type (standard / bump / xu / dual / customized-coef, os-emf-solver-fei.f03:2064-2329): n_coef values
+  // for dB/dt (coef_e) and dE/dt (coef_b) in field precision.  Guard cells as min_gc_fei (:1995-2026),
+  // stability as test_stability_fei for a given set of coefficients (:1370-1384).
+  bool solver_custom = false;
+  SolverCoef<T> solver_coef;
+  int emf_set_solver(int type, int n_coef, const void *coef_e, const void *coef_b) override {
+    if (type == OSGPU_SOLVER_YEE) { solver_custom = false; return OSGPU_OK; }
+    if (type != OSGPU_SOLVER_CUSTOM) { set_error("unknown field solver %d", type); return OSGPU_ERR_INVALID; }
+    if (n_coef < 1 || n_coef > SOLVER_MAX_NCOEF || !coef_e || !coef_b) {
+      set_error("custom solver: n_coef = %d outside 1..%d, or null coefficients", n_coef, SOLVER_MAX_NCOEF);
+      return OSGPU_ERR_INVALID;
+    }
+    const int need_lo = 2 * n_coef - 1, need_up = 2 * n_coef;
+    if (cfg.gc_emf[0][0] < need_lo || cfg.gc_emf[1][0] < need_up || cfg.gc_jay[0][0] < n_coef - 1 || cfg.gc_jay[1][0] < n_coef) {
+      set_error("custom solver with n_coef = %d needs x1 guard cells (%d,%d) on E/B and (%d,%d) on J, has (%d,%d) / (%d,%d)", n_coef,
+                need_lo, need_up, n_coef - 1, n_coef, cfg.gc_emf[0][0], cfg.gc_emf[1][0], cfg.gc_jay[0][0], cfg.gc_jay[1][0]);
+      return OSGPU_ERR_INVALID;
+    }
+    const T *ce = static_cast<const T *>(coef_e), *cb = static_cast<const T *>(coef_b);
+    double se = 0, sb = 0;
+    for (int k = 0; k < n_coef; k++) { se += fabs((double)ce[k]); sb += fabs((double)cb[k]); }
+    double cour = se * sb / (cfg.dx[0] * cfg.dx[0]);
+    for (int d = 1; d < dim; d++) cour += 1.0 / (cfg.dx[d] * cfg.dx[d]);
+    cour = sqrt(1.0 / cour);
+    if (cfg.dt > cour) {
+      set_error("Customized (Fei) EMF solver stability condition violated: dt = %g > dt(CFL) = %g", cfg.dt, cour);
+      return OSGPU_ERR_STABILITY;
+    }
+    solver_coef.n = n_coef;
+    for (int k = 0; k < SOLVER_MAX_NCOEF; k++) {
+      solver_coef.ce[k] = k < n_coef ? ce[k] : T(0);
+      solver_coef.cb[k] = k < n_coef ? cb[k] : T(0);
+    }
+    solver_custom = true;
+    return OSGPU_OK;
+  }
 
   // setup_smooth's result (vdf/os-vdf-smooth.f90:373-467): order(1:D) and scoef(2*max_order+1, D)
   // in field precision, centre at max_order + 1.  The filtered current must cover 1..nx+1 (Yee):
@@ -1419,6 +1461,10 @@ int osgpu_particles_update_boundary(osgpu_sim *h) { H_CHECK(h); return h->impl->
 int osgpu_sort(osgpu_sim *h) { H_CHECK(h); return h->impl->sort(); }
 int osgpu_current_update_boundary(osgpu_sim *h) { H_CHECK(h); return h->impl->current_update_boundary(); }
 int osgpu_emf_advance(osgpu_sim *h) { H_CHECK(h); return h->impl->emf_advance(); }
+int osgpu_emf_set_solver(osgpu_sim *h, int type, int n_coef, const void *coef_e, const void *coef_b) {
+  H_CHECK(h);
+  return h->impl->emf_set_solver(type, n_coef, coef_e, coef_b);
+}
 int osgpu_current_set_smooth(osgpu_sim *h, const int *order, int max_order, const void *scoef) {
   H_CHECK(h);
   if (!order) { osgpu::set_error("smooth: order is null"); return OSGPU_ERR_INVALID; }

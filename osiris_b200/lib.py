@@ -87,6 +87,7 @@ def load():
                  "osgpu_emf_update_particle_fld"):
         getattr(L, name).argtypes = [vp]
     L.osgpu_current_set_smooth.argtypes = [vp, vp, C.c_int, vp]
+    L.osgpu_emf_set_solver.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.osgpu_emf_set_smooth.argtypes = [vp, vp, C.c_int, vp]
     L.osgpu_advance_deposit.argtypes = [vp, dp]
     L.osgpu_field_energy.argtypes = [vp, dp]
@@ -150,5 +151,5 @@ EXPORTS = [
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
     "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release", "osgpu_species_accelerate",
-    "osgpu_species_energy",
+    "osgpu_species_energy", "osgpu_emf_set_solver",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -264,6 +264,15 @@ class _Emf:
         order[:self.sim.dim] = smooth.order
         check(self.sim._L.osgpu_emf_set_smooth(self.sim._h, ptr(order), int(smooth.max_order), ptr(sc)))
 
+    def set_solver(self, solver):
+        """el_mag_fld{ solver = "yee" | "custom" } + emf_solver{...}: an osiris_b200.solver.Solver"""
+        dt = self.sim.dtype
+        if solver is None or solver.name == "yee":
+            check(self.sim._L.osgpu_emf_set_solver(self.sim._h, 0, 0, None, None))
+            return
+        ce, cb = np.ascontiguousarray(solver.coef_e, dt), np.ascontiguousarray(solver.coef_b, dt)
+        check(self.sim._L.osgpu_emf_set_solver(self.sim._h, 1, int(solver.n_coef), ptr(ce), ptr(cb)))
+
     def update_particle_fld(self):
         """update_particle_fld (emf/os-emf.f03:1065-1150): refresh e_part / b_part"""
         check(self.sim._L.osgpu_emf_update_particle_fld(self.sim._h))
@@ -338,7 +347,7 @@ class Simulation:
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
                  node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None,
-                 emf_smooth=None, part_bc=None, if_move=None):
+                 emf_smooth=None, part_bc=None, if_move=None, solver=None):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
@@ -348,6 +357,9 @@ class Simulation:
         if emf_smooth is not None:
             smooth_order = max(smooth_order, emf_smooth.smooth_order())
         glo, gup = min_gc_axes(dim, self.order, smooth_order, if_move)
+        if solver is not None:  # the solver's stencil may need more (os-simulation.f03:360-365)
+            slo, sup = solver.min_gc(dim)
+            glo, gup = [max(a, b) for a, b in zip(glo, slo)], [max(a, b) for a, b in zip(gup, sup)]
         self.gc_emf = gc_emf if gc_emf is not None else (list(glo), list(gup))
         self.gc_jay = gc_jay if gc_jay is not None else (list(glo), list(gup))
         if smooth is not None and gc_jay is None:  # setup of t_current (current/os-current-define.f03:192-205)
@@ -390,6 +402,8 @@ class Simulation:
             self.jay.set_smooth(smooth)
         if emf_smooth is not None:
             self.emf.set_smooth(emf_smooth)
+        if solver is not None:
+            self.emf.set_solver(solver)
 
     # padded host array shapes (numpy order: slowest first, component last)
     def _shape(self, gc):

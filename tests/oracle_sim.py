@@ -8,7 +8,7 @@ from oracle.bindings import Oracle, aligned
 
 class OracleSim:
     def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None, emf_smooth=None,
-                 periodic=None, part_bc=None, window_order="device"):
+                 periodic=None, part_bc=None, window_order="device", solver=None):
         self.orc = Oracle(precision)
         self.dtype = self.orc.dtype
         self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
@@ -34,6 +34,7 @@ class OracleSim:
         # particles use dt rounded to their precision (spec/os-spec-vpush.f03:374)
         self.dtp = float(self.dtype(self.dt))
         self.n = 0  # n(tstep)
+        self.solver = solver  # osiris_b200.solver.Solver or None (Yee)
 
     def add_species(self, rqm, ix, x, p, q, tag=None, udist=None):
         sp = dict(rqm=float(rqm), udist=udist, ix=np.ascontiguousarray(ix, np.int32).copy(),
@@ -119,6 +120,10 @@ class OracleSim:
 
     def emf_advance(self):
         assert self.gc_emf == self.gc_jay
+        if self.solver is not None and self.solver.name == "custom":
+            self.orc.fei_advance(self.dim, self.e, self.b, self.j, self.nx, self.gc_emf, self.dx, self.dt,
+                                 self.solver.coef_e, self.solver.coef_b)
+            return
         self.orc.yee_advance(self.dim, self.e, self.b, self.j, self.nx, self.gc_emf, self.dx, self.dt)
 
     def iter(self, nsteps=1):

@@ -79,7 +79,19 @@ typedef struct osgpu_config {
    * the rank that topology gives those coordinates. */
   int32_t topology;
   int32_t neighbor[2][OSGPU_MAX_DIM]; /* [lower|upper][axis] NCCL rank, -1 none (OSGPU_TOPO_HOST) */
+  /* field boundary condition at a physical wall, [lower|upper][axis]: emf_bound{ type } (emf/boundary/
+   * os-emf-boundary.f90:204-384).  OSGPU_EBC_NONE: nothing is done (periodic / other node / moving window,
+   * p_bc_move_c); OSGPU_EBC_PEC ("pec", "conducting") and OSGPU_EBC_PMC ("pmc", "reflecting"): the mirror
+   * walls of os-emf-pec.f90 / os-emf-pmc.f90 after every B and E (sub)step of the solver, in the variant
+   * the particle interpolation selects (odd orders: wall on the cell edge, even: through the cell centre,
+   * :490-511), and the specular fold of the current at the same wall (current/os-current-boundary.f03;
+   * t_current takes its boundary type from emf_bound, current/os-current-define.f03:240-251).  Pair it with
+   * part_bc = OSGPU_PBC_SPECULAR for the particles.  Open walls (lindman, vpml) are not built. */
+  int32_t emf_bc[2][OSGPU_MAX_DIM];
 } osgpu_config;
+#define OSGPU_EBC_NONE 0
+#define OSGPU_EBC_PEC 1
+#define OSGPU_EBC_PMC 2
 #define OSGPU_PBC_ABSORB 0
 #define OSGPU_PBC_SPECULAR 1
 #define OSGPU_TOPO_MPI 0
@@ -106,6 +118,14 @@ int osgpu_exchange_ranges(int nx, int gcl, int gcu, int mode, int32_t *out8);
  * ranges slide down so the upper neighbour also refreshes the cells the shift pulled out of stale
  * guard cells (nx_move argument of isend_vdf / irecv_vdf, vdf/os-vdf-comm.f90:770-776, 880-887) */
 int osgpu_exchange_ranges_move(int nx, int gcl, int gcu, int mode, int nx_move, int32_t *out8);
+/* the mirror rule the device applies at a PEC / PMC wall of `axis` (0-based), side 0 lower / 1 upper, to the
+ * three components of E (is_b = 0) or B, and to J for an interpolation order: per component
+ * {m, s, lo, hi, plane, plane_op} -- guard cells i = lo..hi take s * f(m - i) (fields) or are added with sign s
+ * onto cell m - i (current); `plane` (INT32_MIN: none) is set to zero (plane_op 1) or doubled (2).  Restates
+ * pec_bc_* / pmc_bc_* (emf/boundary/os-emf-pec.f90, os-emf-pmc.f90) and spec_bc_* (current/
+ * os-current-boundary.f03); exported so the rule can be checked against those statements without a GPU. */
+int osgpu_field_wall_op(int nx, int axis, int side, int is_b, int pmc, int even, int gcl, int gcu, int32_t *out18);
+int osgpu_current_wall_op(int nx, int axis, int side, int order, int32_t *out18);
 /* minimum guard cells the particles need for an interpolation order
  * (particles/os-particles.f03:329-346) merged with the Yee solver's (1,2)
  * (emf/solver/os-emf-solver-yee.f03:458-468): out = {lower, upper} */

@@ -10,6 +10,8 @@
 #include <utility>
 
 #include "common.cuh"
+#include <limits.h>
+
 #include "fields.cuh"
 
 namespace osgpu {
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(128)
 }
 
 template <typename T>
-int yee_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+int yee_substep(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt, int sub,
                 cudaStream_t st, long long *launches) {
   // advance_yee: B half step, E full step, B half step (os-emf-solver-yee.f03:542-568);
   // dtdx = real(dt/dx, p_k_fld) with the full-precision dt (:223-225, :398-401)
@@ -80,18 +82,26 @@ int yee_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const do
   const dim3 gb((g.nx[0] + 2 + 127) / 128, g.nx[1] + 2, g.dim == 3 ? g.nx[2] + 2 : 1);
   const dim3 ge((g.nx[0] + 1 + 127) / 128, g.nx[1] + 1, g.dim == 3 ? g.nx[2] + 1 : 1);
   if (g.dim == 2) {
-    yee_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
-    yee_e_kernel<2, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif);
-    yee_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+    if (sub != 1) yee_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+    else yee_e_kernel<2, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif);
   } else {
-    yee_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
-    yee_e_kernel<3, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif);
-    yee_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+    if (sub != 1) yee_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3);
+    else yee_e_kernel<3, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif);
   }
-  *launches += 3;
+  *launches += 1;
   OSGPU_CUDA(cudaGetLastError());
   return OSGPU_OK;
 }
+template <typename T>
+int yee_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+                cudaStream_t st, long long *launches) {
+  for (int sub = 0; sub < 3; sub++) OSGPU_TRY(yee_substep<T>(g, e, b, jay, dx, dt, sub, st, launches));
+  return OSGPU_OK;
+}
+template int yee_substep<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>, const double *, double, int,
+                                cudaStream_t, long long *);
+template int yee_substep<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>, const double *, double, int,
+                                 cudaStream_t, long long *);
 template int yee_advance<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>,
                                 const double *, double, cudaStream_t, long long *);
 template int yee_advance<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>,
@@ -158,8 +168,8 @@ __global__ void __launch_bounds__(128)
 }
 
 template <typename T>
-int fei_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
-                const SolverCoef<T> &sc, cudaStream_t st, long long *launches) {
+int fei_substep(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+                const SolverCoef<T> &sc, int sub, cudaStream_t st, long long *launches) {
   const double dtb = dt / 2.0;
   const T hb1 = (T)(dtb / dx[0]), hb2 = (T)(dtb / dx[1]), hb3 = (g.dim == 3) ? (T)(dtb / dx[2]) : T(0);
   const T he1 = (T)(dt / dx[0]), he2 = (T)(dt / dx[1]), he3 = (g.dim == 3) ? (T)(dt / dx[2]) : T(0);
@@ -169,22 +179,150 @@ int fei_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const do
   const dim3 gb((g.nx[0] + 2 * sc.n + 127) / 128, g.nx[1] + 2, g.dim == 3 ? g.nx[2] + 2 : 1);
   const dim3 ge((g.nx[0] + 2 * sc.n - 1 + 127) / 128, g.nx[1] + 1, g.dim == 3 ? g.nx[2] + 1 : 1);
   if (g.dim == 2) {
-    fei_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
-    fei_e_kernel<2, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif, sc);
-    fei_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+    if (sub != 1) fei_b_kernel<2, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+    else fei_e_kernel<2, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif, sc);
   } else {
-    fei_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
-    fei_e_kernel<3, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif, sc);
-    fei_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+    if (sub != 1) fei_b_kernel<3, T><<<gb, blk, 0, st>>>(b, ce, g, hb1, hb2, hb3, sc);
+    else fei_e_kernel<3, T><<<ge, blk, 0, st>>>(e, cb, cj, g, he1, he2, he3, dtif, sc);
   }
-  *launches += 3;
+  *launches += 1;
   OSGPU_CUDA(cudaGetLastError());
   return OSGPU_OK;
 }
+template <typename T>
+int fei_advance(const Grid &g, Field3<T> e, Field3<T> b, Field3<T> jay, const double *dx, double dt,
+                const SolverCoef<T> &sc, cudaStream_t st, long long *launches) {
+  for (int sub = 0; sub < 3; sub++) OSGPU_TRY(fei_substep<T>(g, e, b, jay, dx, dt, sc, sub, st, launches));
+  return OSGPU_OK;
+}
+template int fei_substep<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>, const double *, double,
+                                const SolverCoef<float> &, int, cudaStream_t, long long *);
+template int fei_substep<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>, const double *, double,
+                                 const SolverCoef<double> &, int, cudaStream_t, long long *);
 template int fei_advance<float>(const Grid &, Field3<float>, Field3<float>, Field3<float>, const double *, double,
                                 const SolverCoef<float> &, cudaStream_t, long long *);
 template int fei_advance<double>(const Grid &, Field3<double>, Field3<double>, Field3<double>, const double *, double,
                                  const SolverCoef<double> &, cudaStream_t, long long *);
+
+// ---------------------------------------------------------------------------------------------
+// Mirror walls.  One thread per point of the wall plane (all padded cells of the other two axes, as
+// the reference loops over the whole extent of the t_vdf there), each walking the few guard cells of
+// the three components along the wall axis.
+// ---------------------------------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(128) wall_kernel(Field3<T> f, Grid g, WallOp op) {
+  const int a = op.axis;
+  const int u = (a == 0) ? 1 : 0, v = (a == 2) ? 1 : 2;  // the other two axes
+  const int iu = blockIdx.x * blockDim.x + threadIdx.x, iv = blockIdx.y;
+  if (iu >= g.S[u] || iv >= g.S[v]) return;
+  const long long stride = (a == 0) ? 1 : (a == 1 ? (long long)g.P0 : (long long)g.P0 * g.S[1]);
+  int q[3] = {0, 0, 0};
+  q[u] = iu;
+  q[v] = iv;
+  const long long base = g.at(q[0], q[1], q[2]) + (long long)(g.gl[a] - 1) * stride;  // cell 0 -> + i * stride
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const WallComp w = op.c[c];
+    T *p = f.c[c] + base;
+    if (op.fold) {
+      for (int i = w.lo; i <= w.hi; i++) {
+        const T src = p[i * stride];
+        T *dst = p + (long long)(w.m - i) * stride;
+        *dst = (w.s > 0) ? *dst + src : *dst - src;
+      }
+    } else {
+      for (int i = w.lo; i <= w.hi; i++) {
+        const T src = p[(long long)(w.m - i) * stride];
+        p[i * stride] = (w.s > 0) ? src : -src;
+      }
+    }
+    if (w.plane != INT_MIN) {
+      T *pp = p + (long long)w.plane * stride;
+      *pp = (w.plane_op == 1) ? T(0) : *pp * T(2);
+    }
+  }
+}
+
+// The reference's odd / even and PEC / PMC routines are one rule: a component sits at cell index i + o/2
+// along the wall axis (E: o = 1 for the normal component, B: o = 1 for the tangential ones), the mirror
+// plane at P/2 (wall on a cell edge, "odd": P = 2 | 2 nx + 2; through the cell centres, "even": P = 1 |
+// 2 nx + 1), so cell i maps to m - i with m = P - o; the guard cells beyond the plane take s times their
+// image, and a point on the plane (m even) is zero when s = -1.  PEC: normal E and tangential B even
+// (s = +1), tangential E and normal B odd; PMC the other way round.  One exception is kept as the
+// reference has it: pec_bc_b_*_odd starts the upper tangential loop at nx + 2 (os-emf-pec.f90:590-600).
+WallOp field_wall_op(const Grid &g, int axis, int side, int is_b, int pmc, int even, const int gc[2][3]) {
+  WallOp op;
+  op.axis = axis;
+  op.fold = 0;
+  const int nx = g.nx[axis];
+  const int P = side == 0 ? (even ? 1 : 2) : (even ? 2 * nx + 1 : 2 * nx + 2);
+  for (int c = 0; c < 3; c++) {
+    const bool normal = (c == axis);
+    const int o = is_b ? !normal : normal;
+    int s = is_b ? (normal ? -1 : +1) : (normal ? +1 : -1);
+    if (pmc) s = -s;
+    WallComp w;
+    w.m = P - o;
+    w.s = s;
+    w.plane = INT_MIN;
+    w.plane_op = 0;
+    const bool on_plane = (w.m % 2 == 0);
+    if (side == 0) {
+      w.lo = 1 - gc[0][axis];
+      w.hi = on_plane ? w.m / 2 - 1 : (w.m - 1) / 2;
+    } else {
+      w.hi = nx + gc[1][axis];
+      w.lo = on_plane ? w.m / 2 + 1 : (w.m + 1) / 2;
+      if (!pmc && !even && is_b && !normal) w.lo += 1;
+    }
+    if (on_plane && s < 0) { w.plane = w.m / 2; w.plane_op = 1; }
+    op.c[c] = w;
+  }
+  return op;
+}
+// spec_bc_2d / spec_bc_3d: the same mirror (plane on the cell edge for odd interpolation orders, through
+// the cell centres for even ones) applied as a fold: what was deposited beyond the wall is added to its
+// image with s = -1 for the component along the wall normal, +1 for the others; on the plane the normal
+// component is zero and the others doubled.  Guard cells that can hold current: order/2 + 1 below the
+// wall, (order+1)/2 + 1 above it (one less for the normal component, which sits half a cell higher).
+WallOp current_wall_op(const Grid &g, int axis, int side, int order) {
+  WallOp op;
+  op.axis = axis;
+  op.fold = 1;
+  const int nx = g.nx[axis];
+  const bool even = (order % 2 == 0);
+  const int P = side == 0 ? (even ? 1 : 2) : (even ? 2 * nx + 1 : 2 * nx + 2);
+  const int Lg = order / 2 + 1, Lu = (order + 1) / 2 + 1;
+  for (int c = 0; c < 3; c++) {
+    const bool normal = (c == axis);
+    WallComp w;
+    w.m = P - (normal ? 1 : 0);
+    w.s = normal ? -1 : +1;
+    w.plane = INT_MIN;
+    w.plane_op = 0;
+    const bool on_plane = (w.m % 2 == 0);
+    if (side == 0) {
+      w.lo = 1 - Lg;
+      w.hi = on_plane ? w.m / 2 - 1 : (w.m - 1) / 2;
+    } else {
+      w.hi = nx + Lu - (normal ? 1 : 0);
+      w.lo = on_plane ? w.m / 2 + 1 : (w.m + 1) / 2;
+    }
+    if (on_plane) { w.plane = w.m / 2; w.plane_op = normal ? 1 : 2; }
+    op.c[c] = w;
+  }
+  return op;
+}
+template <typename T> int wall_apply(const Grid &g, Field3<T> f, const WallOp &op, cudaStream_t st, long long *launches) {
+  const int a = op.axis;
+  const int u = (a == 0) ? 1 : 0, v = (a == 2) ? 1 : 2;
+  const dim3 grid((g.S[u] + 127) / 128, g.S[v]);
+  wall_kernel<T><<<grid, 128, 0, st>>>(f, g, op);
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int wall_apply<float>(const Grid &, Field3<float>, const WallOp &, cudaStream_t, long long *);
+template int wall_apply<double>(const Grid &, Field3<double>, const WallOp &, cudaStream_t, long long *);
 
 // ---------------------------------------------------------------------------------------------
 // Current smoothing: one pass of the separable digital filter along `axis`, src -> dst

@@ -354,6 +354,7 @@ template <typename T> struct Sim final : SimBase {
       for (auto &b : xbuf) OSGPU_CUDA(cudaMalloc(&b, xbuf_elems * sizeof(T)));
     }
     sp.resize(std::max(0, (int)c->nspecies));
+    OSGPU_TRY(setup_walls());
     OSGPU_CUDA(cudaStreamSynchronize(st));
     return OSGPU_OK;
   }
@@ -888,11 +889,49 @@ template <typename T> struct Sim final : SimBase {
   }
   int current_update_boundary() override {
     T *comps[3] = {J.c[0], J.c[1], J.c[2]};
-    return update_guards(comps, 3, 1);
+    OSGPU_TRY(update_guards(comps, 3, 1));
+    // specular fold at PEC / PMC walls (update_boundary_current, current/os-current-define.f03:708-723)
+    for (const Wall &w : walls) OSGPU_TRY(wall_apply<T>(g, J, current_wall_op(g, w.axis, w.side, order), st, &launches));
+    return OSGPU_OK;
+  }
+  // physical walls with a field boundary condition: (axis, side, pmc) in the reference's loop order
+  struct Wall { int axis, side, pmc; };
+  std::vector<Wall> walls;
+  int setup_walls() {
+    walls.clear();
+    for (int d = 0; d < dim; d++)
+      for (int sd = 0; sd < 2; sd++) {
+        const int t = cfg.emf_bc[sd][d];
+        if (t == OSGPU_EBC_NONE) continue;
+        if (t != OSGPU_EBC_PEC && t != OSGPU_EBC_PMC) { set_error("emf_bc[%d][%d] = %d: unknown field boundary condition", sd, d, t); return OSGPU_ERR_INVALID; }
+        if (cfg.periodic[d]) { set_error("emf_bc on the periodic axis %d", d); return OSGPU_ERR_INVALID; }
+        if (neigh[2 * d + sd] >= 0) continue;  // another rank lies behind this face: p_bc_other_node
+        walls.push_back({d, sd, t == OSGPU_EBC_PMC});
+      }
+    return OSGPU_OK;
+  }
+  // update_boundary_bfld / _efld_emf_bound (emf/boundary/os-emf-boundary.f90:840-1112): PEC / PMC walls
+  int field_walls(Field3<T> f, int is_b) {
+    for (const Wall &w : walls)
+      OSGPU_TRY(wall_apply<T>(g, f, field_wall_op(g, w.axis, w.side, is_b, w.pmc, order % 2 == 0, cfg.gc_emf), st, &launches));
+    return OSGPU_OK;
   }
   int emf_advance() override {
-    if (solver_custom) return fei_advance<T>(g, E, B, J, cfg.dx, cfg.dt, solver_coef, st, &launches);
-    return yee_advance<T>(g, E, B, J, cfg.dx, cfg.dt, st, &launches);
+    if (solver_custom) {
+      for (const Wall &w : walls)
+        if (w.axis == 0) { set_error("the customized solver at an x1 wall needs boundary tapering (taper_bnd), which is not built"); return OSGPU_ERR_INVALID; }
+    }
+    if (walls.empty()) {
+      if (solver_custom) return fei_advance<T>(g, E, B, J, cfg.dx, cfg.dt, solver_coef, st, &launches);
+      return yee_advance<T>(g, E, B, J, cfg.dx, cfg.dt, st, &launches);
+    }
+    // advance_yee / advance_fei with the wall hooks between the substeps (os-emf-solver-yee.f03:542-568)
+    for (int sub = 0; sub < 3; sub++) {
+      if (solver_custom) OSGPU_TRY(fei_substep<T>(g, E, B, J, cfg.dx, cfg.dt, solver_coef, sub, st, &launches));
+      else OSGPU_TRY(yee_substep<T>(g, E, B, J, cfg.dx, cfg.dt, sub, st, &launches));
+      OSGPU_TRY(field_walls(sub == 1 ? E : B, sub != 1));
+    }
+    return OSGPU_OK;
   }
   // el_mag_fld{ solver = "yee" | "custom" } (new_solver_emf, emf/solver/os-emf-solver.f03:36-52).  The
   // customized solver takes the stencil coefficients read_input_fei ends up with, whatever their
@@ -1408,6 +1447,33 @@ int osgpu_exchange_ranges_move(int nx, int gcl, int gcu, int mode, int nx_move, 
     o[4] = 1 - gcl;      o[5] = gcu;
     o[6] = nx + 1 - gcl; o[7] = nx + gcu;
   }
+  return OSGPU_OK;
+}
+// the mirror-wall rule as the kernels apply it, per component {m, s, lo, hi, plane, plane_op} (fields.cuh: WallComp)
+static void wall_op_out(const WallOp &op, int32_t *out18) {
+  for (int c = 0; c < 3; c++) {
+    const WallComp &w = op.c[c];
+    const int32_t v[6] = {w.m, w.s, w.lo, w.hi, w.plane, w.plane_op};
+    for (int k = 0; k < 6; k++) out18[6 * c + k] = v[k];
+  }
+}
+int osgpu_field_wall_op(int nx, int axis, int side, int is_b, int pmc, int even, int gcl, int gcu, int32_t *out18) {
+  if (axis < 0 || axis > 2 || !out18) return OSGPU_ERR_INVALID;
+  Grid g;
+  memset(&g, 0, sizeof g);
+  g.nx[axis] = nx;
+  int gc[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  gc[0][axis] = gcl;
+  gc[1][axis] = gcu;
+  wall_op_out(field_wall_op(g, axis, side, is_b, pmc, even, gc), out18);
+  return OSGPU_OK;
+}
+int osgpu_current_wall_op(int nx, int axis, int side, int order, int32_t *out18) {
+  if (axis < 0 || axis > 2 || order < 1 || order > 4 || !out18) return OSGPU_ERR_INVALID;
+  Grid g;
+  memset(&g, 0, sizeof g);
+  g.nx[axis] = nx;
+  wall_op_out(current_wall_op(g, axis, side, order), out18);
   return OSGPU_OK;
 }
 int osgpu_min_gc(int order, int32_t *out2) {

@@ -30,7 +30,7 @@ class Config(C.Structure):
         ("node_dims", C.c_int32 * 3), ("node_coords", C.c_int32 * 3), ("periodic", C.c_int32 * 3),
         ("rank", C.c_int32), ("nranks", C.c_int32), ("device", C.c_int32), ("smooth_order", C.c_int32),
         ("no_tags", C.c_int32), ("part_bc", (C.c_int32 * 3) * 2),
-        ("topology", C.c_int32), ("neighbor", (C.c_int32 * 3) * 2),
+        ("topology", C.c_int32), ("neighbor", (C.c_int32 * 3) * 2), ("emf_bc", (C.c_int32 * 3) * 2),
     ]
 
 
@@ -59,6 +59,8 @@ def load():
     L.osgpu_exchange_ranges.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.osgpu_exchange_ranges_move.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     L.osgpu_min_gc.argtypes = [C.c_int, i32p]
+    L.osgpu_field_wall_op.argtypes = [C.c_int] * 8 + [i32p]
+    L.osgpu_current_wall_op.argtypes = [C.c_int] * 4 + [i32p]
     L.osgpu_nccl_unique_id.argtypes = [vp]
     L.osgpu_init.argtypes = [C.POINTER(vp), C.POINTER(Config), vp]
     L.osgpu_finalize.argtypes = [vp]
@@ -151,5 +153,5 @@ EXPORTS = [
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
     "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release", "osgpu_species_accelerate",
-    "osgpu_species_energy", "osgpu_emf_set_solver",
+    "osgpu_species_energy", "osgpu_emf_set_solver", "osgpu_field_wall_op", "osgpu_current_wall_op",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -347,7 +347,7 @@ class Simulation:
 
     def __init__(self, dim, interpolation, nx, dx, dt, precision="f32", nspecies=1, gc_emf=None, gc_jay=None,
                  node_conf=None, nccl_id=None, device=-1, smooth_order=0, add_tag=True, smooth=None,
-                 emf_smooth=None, part_bc=None, if_move=None, solver=None):
+                 emf_smooth=None, part_bc=None, if_move=None, solver=None, emf_bc=None):
         self._L = _lib.load()
         self.dim, self.order = int(dim), int(interpolation)
         self.dtype = np.float32 if precision in ("f32", 4, np.float32) else np.float64
@@ -388,6 +388,13 @@ class Simulation:
             for s_ in range(2):
                 for d in range(dim):
                     cfg.part_bc[s_][d] = {"absorbing": 0, "specular": 1}[part_bc[s_][d]]
+        # field boundary condition at physical walls, ([lower per axis], [upper per axis]) of emf_bound{ type }:
+        # "none" | "conducting" ("pec") | "reflecting" ("pmc"); the current is folded at the same walls
+        if emf_bc is not None:
+            names = {"none": 0, "conducting": 1, "pec": 1, "reflecting": 2, "pmc": 2}
+            for s_ in range(2):
+                for d in range(dim):
+                    cfg.emf_bc[s_][d] = names[emf_bc[s_][d]]
         self.add_tag = bool(add_tag)
         self._cfg = cfg
         self._h = C.c_void_p()

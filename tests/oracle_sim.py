@@ -8,7 +8,7 @@ from oracle.bindings import Oracle, aligned
 
 class OracleSim:
     def __init__(self, dim, order, nx, dx, dt, precision="f32", gc_emf=None, gc_jay=None, smooth=None, emf_smooth=None,
-                 periodic=None, part_bc=None, window_order="device", solver=None):
+                 periodic=None, part_bc=None, window_order="device", solver=None, emf_bc=None):
         self.orc = Oracle(precision)
         self.dtype = self.orc.dtype
         self.dim, self.order, self.nx, self.dx, self.dt = dim, order, list(nx), list(dx), float(dt)
@@ -35,6 +35,8 @@ class OracleSim:
         self.dtp = float(self.dtype(self.dt))
         self.n = 0  # n(tstep)
         self.solver = solver  # osiris_b200.solver.Solver or None (Yee)
+        # ([lower per axis], [upper per axis]) of "none" | "conducting" | "reflecting" on the non-periodic axes
+        self.emf_bc = emf_bc if emf_bc is not None else (["none"] * dim, ["none"] * dim)
 
     def add_species(self, rqm, ix, x, p, q, tag=None, udist=None):
         sp = dict(rqm=float(rqm), udist=udist, ix=np.ascontiguousarray(ix, np.int32).copy(),
@@ -93,8 +95,17 @@ class OracleSim:
                 if k in sp:
                     sp[k] = np.ascontiguousarray(sp[k][keep])
 
+    def _walls(self):
+        """(axis, side, kind) of the PEC / PMC walls in the reference's loop order"""
+        kinds = {"conducting": "pec", "pec": "pec", "reflecting": "pmc", "pmc": "pmc"}
+        return [(d, sd, kinds[self.emf_bc[sd][d]]) for d in range(self.dim) for sd in range(2)
+                if self.emf_bc[sd][d] != "none" and not self.periodic[d]]
+
     def current_update_boundary(self):
+        from oracle import walls
         self.orc.update_periodic(self.dim, self.j, self.nx, self.gc_jay, "add", axes=self._paxes())
+        for d, sd, _ in self._walls():   # update_boundary_current (current/os-current-define.f03:708-723)
+            walls.current_wall(self.j, self.dim, d, sd, self.order, self.nx, self.gc_jay[0])
 
     def move_window(self, nmove):
         """emf%move_window + part%move_window (os-simulation.f03:529-548)"""
@@ -120,6 +131,18 @@ class OracleSim:
 
     def emf_advance(self):
         assert self.gc_emf == self.gc_jay
+        if self._walls():
+            # advance_yee with the wall hooks (emf/solver/os-emf-solver-yee.f03:542-568)
+            from oracle import walls
+            assert self.solver is None or self.solver.name == "yee"
+            parity = "odd" if self.order % 2 == 1 else "even"   # init_emf_bound, os-emf-boundary.f90:490-511
+            def hook(f, which):
+                for d, sd, kind in self._walls():
+                    walls.field_wall(f, which, kind, parity, self.dim, d, sd, self.nx, self.gc_emf[0])
+            self.orc.dbdt(self.dim, self.b, self.e, self.nx, self.gc_emf, self.dx, self.dt / 2.0); hook(self.b, "b")
+            self.orc.dedt(self.dim, self.e, self.b, self.j, self.nx, self.gc_emf, self.dx, self.dt); hook(self.e, "e")
+            self.orc.dbdt(self.dim, self.b, self.e, self.nx, self.gc_emf, self.dx, self.dt / 2.0); hook(self.b, "b")
+            return
         if self.solver is not None and self.solver.name == "custom":
             self.orc.fei_advance(self.dim, self.e, self.b, self.j, self.nx, self.gc_emf, self.dx, self.dt,
                                  self.solver.coef_e, self.solver.coef_b)

@@ -220,6 +220,13 @@ int osgpu_species_accelerate(osgpu_sim *sim, int sp_id, double u_frac, double q_
 /* energy sum of the species' last push (this%energy(1), spec/os-spec-define.f03:1030-1086; multiply by
  * rqm * cell volume for get_energy) */
 int osgpu_species_energy(osgpu_sim *sim, int sp_id, double *ene);
+/* replaces: deposit_rho (spec/os-spec-charge.f90:139-197, templates :463-589) followed by the guard-cell
+ * sum update_boundary(rho, p_vdf_add) of the charge diagnostics: the species' charge density on the grid
+ * nodes, rho(i + k) += q prod S(k) with the species' interpolation order.  rho is the host array
+ * rho(1, S1, S2[, S3]) with the guard cells of the J array (or NULL: keep the sum on the device);
+ * accumulate != 0 adds this species to the density the previous call left (total charge).  The species
+ * must not have unprocessed leavers (call it after osgpu_species_update_boundary / osgpu_step). */
+int osgpu_species_deposit_charge(osgpu_sim *sim, int sp_id, void *rho, int accumulate);
 int osgpu_sort(osgpu_sim *sim);                      /* spec/os-species.f03:269-332           */
 int osgpu_current_update_boundary(osgpu_sim *sim); /* current/os-current-define.f03:683-727 */
 int osgpu_emf_advance(osgpu_sim *sim);

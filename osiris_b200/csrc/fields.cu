@@ -628,4 +628,17 @@ int field_energy(const Grid &g, T *const *comps6, double *dev_out6, cudaStream_t
 template int field_energy<float>(const Grid &, float *const *, double *, cudaStream_t, long long *);
 template int field_energy<double>(const Grid &, double *const *, double *, cudaStream_t, long long *);
 
+template <typename T> __global__ void __launch_bounds__(256) plane_add_kernel(T *dst, const T *src, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = dst[i] + src[i];
+}
+template <typename T> int plane_add(const Grid &g, T *dst, const T *src, cudaStream_t st, long long *launches) {
+  plane_add_kernel<T><<<(unsigned)((g.vol + 255) / 256), 256, 0, st>>>(dst, src, g.vol);
+  *launches += 1;
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int plane_add<float>(const Grid &, float *, const float *, cudaStream_t, long long *);
+template int plane_add<double>(const Grid &, double *, const double *, cudaStream_t, long long *);
+
 }  // namespace osgpu

@@ -74,6 +74,8 @@ int smooth_field(const Grid &g, Field3<T> src, Field3<T> dst, Field3<T> tmp, con
 template <typename T>
 int shift_field(const Grid &g, Field3<T> f, Field3<T> tmp, const SmoothBox &bx, const int *nmove, cudaStream_t st,
                 long long *launches);
+// dst += src over one padded plane
+template <typename T> int plane_add(const Grid &g, T *dst, const T *src, cudaStream_t st, long long *launches);
 template <typename T>
 int field_energy(const Grid &g, T *const *comps6, double *dev_out6, cudaStream_t st, long long *launches);
 

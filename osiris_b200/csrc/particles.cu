@@ -423,6 +423,67 @@ int movers_unpack(const uint32_t *buf, int nrec, const Grid &g, int axis, int ad
   LAUNCHED(1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// charge density (a diagnostic: one CTA per tile, one thread per particle, global atomics)
+// ---------------------------------------------------------------------------------------------
+template <int DIM, int ORDER, typename T>
+__global__ void __launch_bounds__(256)
+    charge_kernel(SpeciesView<T> sp, const int *tile_off, const int *tile_cnt, Grid g, Tiling tl, T *rho) {
+  constexpr int NP = Stencil<ORDER>::NP, LP = Stencil<ORDER>::LP;
+  const int tile = blockIdx.x;
+  const int n = tile_cnt[tile];
+  const long long off = tile_off[tile];
+  int t = tile, o0[3];
+  o0[0] = (t % tl.nt[0]) * tl.T[0]; t /= tl.nt[0];
+  o0[1] = (t % tl.nt[1]) * tl.T[1]; t /= tl.nt[1];
+  o0[2] = t * tl.T[2];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long s = off + i;
+    const int cell = sp.cell[s];
+    T w[DIM][NP];
+    int b[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      spline<ORDER, T>(sp.r(d, s), w[d]);
+      b[d] = o0[d] + cell_l(cell, d) + g.gl[d] + LP;
+    }
+    const T q = sp.r(DIM + 3, s);
+#pragma unroll
+    for (int k3 = 0; k3 < (DIM == 3 ? NP : 1); k3++)
+#pragma unroll
+      for (int k2 = 0; k2 < NP; k2++)
+#pragma unroll
+        for (int k1 = 0; k1 < NP; k1++) {
+          T v = (q * w[0][k1]) * w[1][k2];
+          if (DIM == 3) v = v * w[DIM - 1][k3];
+          atomicAdd(&rho[g.at(b[0] + k1, b[1] + k2, b[2] + k3)], v);
+        }
+  }
+}
+template <typename T>
+int deposit_charge(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const Grid &g, const Tiling &tl,
+                   int order, T *rho, cudaStream_t st, long long *launches) {
+#define CASE(D, O) \
+  if (g.dim == D && order == O) charge_kernel<D, O, T><<<tl.ntile, 256, 0, st>>>(sp, tile_off, tile_cnt, g, tl, rho);
+  CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 1) CASE(3, 2) CASE(3, 3) CASE(3, 4)
+#undef CASE
+  LAUNCHED(1);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) plane_out_kernel(const T *plane, Grid g, T *out, int hs0, int hs1, int hs2, int hg0, int hg1, int hg2) {
+  const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (r >= (long long)hs0 * hs1 * hs2) return;
+  const int i0 = (int)(r % hs0), i1 = (int)((r / hs0) % hs1), i2 = (int)(r / ((long long)hs0 * hs1));
+  out[r] = plane[g.at(i0 - hg0 + g.gl[0], i1 - hg1 + g.gl[1], i2 - hg2 + g.gl[2])];
+}
+template <typename T>
+int plane_to_host_layout(const Grid &g, const T *plane, T *out, const int *hs, const int *hg, cudaStream_t st,
+                         long long *launches) {
+  const long long n = (long long)hs[0] * hs[1] * hs[2];
+  plane_out_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(plane, g, out, hs[0], hs[1], hs[2], hg[0], hg[1], hg[2]);
+  LAUNCHED(1);
+}
+
 #define INST(T)                                                                                               \
   template int bin_count<T>(const AosParticles<T> &, long long, const Grid &, const Tiling &, const Shift3 &, \
                             int, int *, int *, int *, int *, int *, cudaStream_t, long long *);               \
@@ -445,7 +506,11 @@ int movers_unpack(const uint32_t *buf, int nrec, const Grid &g, int axis, int ad
   template int movers_classify<T>(const MoverView<T> &, const Grid &, int, int, int, uint32_t *, uint32_t *,   \
                                   int *, int, int *, cudaStream_t, long long *);                              \
   template int movers_unpack<T>(const uint32_t *, int, const Grid &, int, int, const MoverView<T> &, int *,    \
-                                cudaStream_t, long long *);
+                                cudaStream_t, long long *);                                                   \
+  template int deposit_charge<T>(const SpeciesView<T> &, const int *, const int *, const Grid &, const Tiling &, \
+                                 int, T *, cudaStream_t, long long *);                                        \
+  template int plane_to_host_layout<T>(const Grid &, const T *, T *, const int *, const int *, cudaStream_t,   \
+                                       long long *);
 INST(float)
 INST(double)
 

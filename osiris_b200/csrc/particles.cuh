@@ -55,6 +55,15 @@ int movers_insert(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const
 template <typename T>
 int relayout(const SpeciesView<T> &src, const int *old_off, const int *tile_cnt, const SpeciesView<T> &dst,
              const int *new_off, const Grid &g, const Tiling &tl, cudaStream_t st, long long *launches);
+// charge density of a species on the grid nodes (deposit_rho, spec/os-spec-charge.f90:139-197, 463-589):
+// rho(i + k) += q prod_d S_d(k_d) with the species' interpolation order, into one device plane (ADDED)
+template <typename T>
+int deposit_charge(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const Grid &g, const Tiling &tl,
+                   int order, T *rho, cudaStream_t st, long long *launches);
+// one padded device plane -> host t_vdf layout f(1, S1h, S2h, S3h) staged on the device
+template <typename T>
+int plane_to_host_layout(const Grid &g, const T *plane, T *out, const int *hsize, const int *hgc, cudaStream_t st,
+                         long long *launches);
 template <typename T> int record_words(int dim);
 template <typename T>
 int movers_classify(const MoverView<T> &mv, const Grid &g, int axis, int send_lo, int send_up, uint32_t *buf_lo,

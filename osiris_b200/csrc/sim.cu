@@ -61,6 +61,7 @@ struct SimBase {
   virtual int species_accelerate(int id, double u_frac, double q_frac, double ufl1, int use_particle_uacc) = 0;
   virtual int species_update_boundary(int id) = 0;
   virtual int species_energy(int id, double *ene) = 0;
+  virtual int species_deposit_charge(int id, void *rho, int accumulate) = 0;
   virtual int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) = 0;
   virtual int sync_all() = 0;
   virtual int move_window(const int *nmove) = 0;
@@ -1141,6 +1142,41 @@ template <typename T> struct Sim final : SimBase {
     return OSGPU_OK;
   }
 
+  // deposit_rho + update_boundary(rho, p_vdf_add) (spec/os-spec-charge.f90:139-197; the charge diagnostics,
+  // spec/diagnostics): the species' charge density on the grid nodes, guard cells summed like the current's,
+  // into the host array rho(1, S1, S2[, S3]) with the J array's guard cells.  accumulate != 0 adds to what the
+  // previous call left on the device (total charge of several species).
+  bool rho_live = false;
+  int species_deposit_charge(int id, void *rho_host, int accumulate) override {
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    Species &s = sp[id];
+    if (s.movers_pending) { set_error("deposit_charge: species %d has unprocessed leavers (call update_boundary first)", id); return OSGPU_ERR_INVALID; }
+    if (!jtmp) OSGPU_CUDA(cudaMalloc(&jtmp, sizeof(T) * 3 * g.vol));
+    T *rho = jtmp, *raw = jtmp + g.vol;  // plane 0: the summed density; plane 1: this call's deposit
+    if (!(accumulate && rho_live)) OSGPU_CUDA(cudaMemsetAsync(rho, 0, sizeof(T) * g.vol, st));
+    OSGPU_CUDA(cudaMemsetAsync(raw, 0, sizeof(T) * g.vol, st));
+    OSGPU_TRY(deposit_charge<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, g, tl, order, raw, st, &launches));
+    T *comps[3] = {raw, raw, raw};
+    OSGPU_TRY(update_guards(comps, 1, 1));
+    OSGPU_TRY(plane_axpy(rho, raw));
+    rho_live = true;
+    if (rho_host) {
+      int hs[3] = {1, 1, 1}, hg[3] = {0, 0, 0};
+      for (int d = 0; d < dim; d++) { hs[d] = g.nx[d] + cfg.gc_jay[0][d] + cfg.gc_jay[1][d]; hg[d] = cfg.gc_jay[0][d]; }
+      const size_t bytes = sizeof(T) * (size_t)hs[0] * hs[1] * hs[2];
+      char *stage = nullptr;
+      OSGPU_TRY(stage_get(bytes, &stage));
+      OSGPU_TRY(plane_to_host_layout<T>(g, rho, (T *)stage, hs, hg, st, &launches));
+      OSGPU_CUDA(cudaMemcpyAsync(rho_host, stage, bytes, cudaMemcpyDeviceToHost, st));
+      OSGPU_CUDA(cudaStreamSynchronize(st));
+    }
+    return OSGPU_OK;
+  }
+  int plane_axpy(T *dst, const T *src) {
+    OSGPU_TRY(plane_add<T>(g, dst, src, st, &launches));
+    return OSGPU_OK;
+  }
+
   int advance_deposit(double *ene) override {
     OSGPU_TRY(current_zero());
     for (size_t i = 0; i < sp.size(); i++)
@@ -1570,6 +1606,10 @@ int osgpu_species_update_boundary(osgpu_sim *h, int id) { H_CHECK(h); return h->
 int osgpu_species_accelerate(osgpu_sim *h, int id, double u_frac, double q_frac, double ufl1, int use_particle_uacc) {
   H_CHECK(h);
   return h->impl->species_accelerate(id, u_frac, q_frac, ufl1, use_particle_uacc);
+}
+int osgpu_species_deposit_charge(osgpu_sim *h, int id, void *rho, int accumulate) {
+  H_CHECK(h);
+  return h->impl->species_deposit_charge(id, rho, accumulate);
 }
 int osgpu_species_energy(osgpu_sim *h, int id, double *ene) {
   H_CHECK(h);

@@ -76,6 +76,7 @@ def load():
     L.osgpu_species_update_boundary.argtypes = [vp, C.c_int]
     L.osgpu_species_accelerate.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
     L.osgpu_species_energy.argtypes = [vp, C.c_int, dp]
+    L.osgpu_species_deposit_charge.argtypes = [vp, C.c_int, vp, C.c_int]
     L.osgpu_current_zero.argtypes = [vp]
     L.osgpu_move_window.argtypes = [vp, vp]
     L.osgpu_species_inject.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
@@ -153,5 +154,5 @@ EXPORTS = [
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
     "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release", "osgpu_species_accelerate",
-    "osgpu_species_energy", "osgpu_emf_set_solver", "osgpu_field_wall_op", "osgpu_current_wall_op",
+    "osgpu_species_energy", "osgpu_species_deposit_charge", "osgpu_emf_set_solver", "osgpu_field_wall_op", "osgpu_current_wall_op",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

@@ -211,6 +211,14 @@ class Species:
         check(self.sim._L.osgpu_species_accelerate(self.sim._h, self.sp_id, float(u_frac), float(q_frac),
                                                    self.udist.ufl[0], int(self.udist.use_particle_uacc)))
 
+    def deposit_charge(self, accumulate=False):
+        """deposit_rho + guard-cell sum (spec/os-spec-charge.f90:139-197): the charge density on the grid nodes,
+        array [(S3,) S2, S1] with the J array's guard cells"""
+        shape = self.sim.jay_shape[:-1]
+        rho = np.zeros(shape, self.sim.dtype)
+        check(self.sim._L.osgpu_species_deposit_charge(self.sim._h, self.sp_id, ptr(rho), int(accumulate)))
+        return rho
+
     @property
     def energy(self):
         """this%energy(1) of the last push (sum q u^2/(gamma+1); get_energy multiplies by rqm * cell volume)"""

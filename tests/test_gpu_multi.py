@@ -181,14 +181,10 @@ def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_
                                                 (2, [2, 1], "upper"), (3, [2, 1, 1], "upper")])
 def test_moving_window_across_ranks(built, tmp_path, dim, node_dims, fill):
     """the window slides through a domain cut along x: the index shift sends one cell column of every
-    rank to its lower neighbour, the lowest rank absorbs, the highest one injects.
-
-    NOT YET RUN GREEN: the first run of this test hung (osgpu_species_inject called the collective
-    particle migration while only the edge rank injects); injection is rank-local since then, but the
-    round's GPU budget was spent before the test could be repeated.  Opt in with OSGPU_TEST_WINDOW_MULTI=1."""
+    rank to its lower neighbour, the lowest rank absorbs, the highest one injects.  fill = "upper": the
+    trailing rank starts in vacuum and fills up one column per move (the LWFA start; a relayout with
+    arrivals on a rank that has no leavers of its own)."""
     world = int(np.prod(node_dims))
-    if os.environ.get("OSGPU_TEST_WINDOW_MULTI") != "1":
-        pytest.skip("multi-rank moving window: opt-in (OSGPU_TEST_WINDOW_MULTI=1), see docstring")
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     from osiris_b200.loads import lattice_species

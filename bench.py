@@ -182,7 +182,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=10, help="untimed steps (>= 3); the default also covers the first "
+                    "cell crossings of the lattice-loaded particles, steps 3-8 run up to 20 %% slower (profiles/r2_steptimes.txt)")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="uniform3d")
     ap.add_argument("--prec", default="f32")

@@ -177,12 +177,12 @@ __global__ void __launch_bounds__(256)
 // then the arrivals per destination tile are counted.
 template <typename T>
 __global__ void __launch_bounds__(256)
-    route_kernel(MoverView<T> mv, int dim, Tiling tl, Grid g, PartBc bc, int *tile_arr, int *errflag) {
+    route_kernel(MoverView<T> mv, int dim, Tiling tl, Grid g, PartBc bc, int *tile_arr, int *errflag, MoverView<T> guests) {
   const int n = min(*mv.count, mv.cap);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     int ix[3] = {1, 1, 1};
     if (mv.ix[0][i] == INT_MIN) continue;  // sent to another rank
-    bool gone = false;
+    bool gone = false, guest = false;
     for (int d = 0; d < dim && !gone; d++) {
       int v = mv.ix[d][i];
       const int side = (v < 1) ? 0 : (v > g.nx[d] ? 1 : -1);
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(256)
         if (type == PBC_WRAP) {
           v += side ? -g.nx[d] : g.nx[d];
         } else if (type == PBC_ABSORB) {
-          gone = true;
+          if (side == 0 && ((bc.defer_lower >> d) & 1u)) guest = true;  // (keeps its index below 1 on this axis)
+          else gone = true;
         } else if (type == PBC_SPECULAR) {
           mv.p[d][i] = -mv.p[d][i];
           mv.x[d][i] = -mv.x[d][i];
@@ -200,6 +201,18 @@ __global__ void __launch_bounds__(256)
         mv.ix[d][i] = v;
       }
       ix[d] = v;
+    }
+    if (guest && !gone) {  // pushed once more from the guest list, then met by the wall like any leaver
+      const int k = atomicAdd(guests.count, 1);
+      if (k < guests.cap) {
+        for (int d = 0; d < dim; d++) { guests.x[d][k] = mv.x[d][i]; guests.ix[d][k] = mv.ix[d][i]; }
+        for (int d = 0; d < 3; d++) guests.p[d][k] = mv.p[d][i];
+        guests.q[k] = mv.q[i];
+        if (guests.tag) guests.tag[k] = mv.tag[i];
+      } else {
+        atomicOr(errflag, ERRF_MOVER_OVERFLOW);
+      }
+      gone = true;
     }
     if (gone) { mv.ix[0][i] = INT_MIN; continue; }
     int t, c;
@@ -389,9 +402,10 @@ int movers_inject(const AosParticles<T> &in, int np, long long tag_base, const G
 }
 template <typename T>
 int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const PartBc &bc, const int *tile_off,
-                 const int *tile_cnt, int *tile_arr, int *errflag, cudaStream_t st, long long *launches) {
+                 const int *tile_cnt, int *tile_arr, int *errflag, const MoverView<T> &guests, cudaStream_t st,
+                 long long *launches) {
   OSGPU_CUDA(cudaMemsetAsync(tile_arr, 0, sizeof(int) * tl.ntile, st));
-  route_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, tl, g, bc, tile_arr, errflag);
+  route_kernel<T><<<GRID_STRIDE_BLOCKS, 256, 0, st>>>(mv, g.dim, tl, g, bc, tile_arr, errflag, guests);
   capacity_kernel<<<(tl.ntile + 255) / 256, 256, 0, st>>>(tile_off, tile_cnt, tile_arr, tl.ntile, errflag);
   LAUNCHED(2);
 }
@@ -498,7 +512,7 @@ int plane_to_host_layout(const Grid &g, const T *plane, T *out, const int *hs, c
   template int movers_download<T>(const MoverView<T> &, long long, const Grid &, int *, T *, T *, T *,         \
                                   long long *, int, cudaStream_t, long long *);                               \
   template int movers_route<T>(const MoverView<T> &, const Grid &, const Tiling &, const PartBc &, const int *, \
-                               const int *, int *, int *, cudaStream_t, long long *);                         \
+                               const int *, int *, int *, const MoverView<T> &, cudaStream_t, long long *);   \
   template int movers_insert<T>(const MoverView<T> &, const Grid &, const Tiling &, const int *, int *,        \
                                 const SpeciesView<T> &, cudaStream_t, long long *);                           \
   template int relayout<T>(const SpeciesView<T> &, const int *, const int *, const SpeciesView<T> &,           \

@@ -23,6 +23,10 @@ struct Shift3 {
 enum : int { PBC_NONE = 0, PBC_WRAP = 1, PBC_ABSORB = 2, PBC_SPECULAR = 3 };
 struct PartBc {
   int t[2][3];
+  // axes whose lower absorbing wall does not remove a particle now but hands it to the species' guest list:
+  // the cells a window move pushed out of the box are pushed once more before the wall takes them
+  // (move_window_species only lowers ix, spec/os-species.f03:171-229; update_boundary comes after the push)
+  unsigned defer_lower;
 };
 
 // upload = counting sort by (tile, cell).  cell_cnt: [ntile][TILE_NCELL] zeroed scratch (counts, then
@@ -48,7 +52,8 @@ int movers_download(const MoverView<T> &mv, long long out_base, const Grid &g, i
                     long long *otag, int by_tag, cudaStream_t st, long long *launches);
 template <typename T>
 int movers_route(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const PartBc &bc, const int *tile_off,
-                 const int *tile_cnt, int *tile_arr, int *errflag, cudaStream_t st, long long *launches);
+                 const int *tile_cnt, int *tile_arr, int *errflag, const MoverView<T> &guests, cudaStream_t st,
+                 long long *launches);
 template <typename T>
 int movers_insert(const MoverView<T> &mv, const Grid &g, const Tiling &tl, const int *tile_off, int *tile_cnt,
                   const SpeciesView<T> &sp, cudaStream_t st, long long *launches);

@@ -941,6 +941,85 @@ template int launch_push_deposit<float>(int, int, const TmaMaps &, const PushArg
 template int launch_push_deposit<double>(int, int, const TmaMaps &, const PushArgs<double> &, int,
                                          cudaStream_t);
 
+// ---------------------------------------------------------------------------------------------
+// list pusher: one thread per particle, fields and current in global memory
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct SixPlanes { const T *eb[6]; T *j[3]; };
+template <int DIM, int ORDER, typename T>
+__global__ void __launch_bounds__(128)
+    push_list_kernel(MoverView<T> in, MoverView<T> out, SixPlanes<T> f, Grid g, PushConst<T> k, double *ene, int *errflag) {
+  constexpr int LP = Stencil<ORDER>::LP;
+  const int n = min(*in.count, in.cap);
+  const long long sy = g.P0, sz = (long long)g.P0 * g.S[1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    T x[DIM], u[3];
+    int ix[DIM], di[3] = {0, 0, 0};
+    Seg<DIM, T> seg[DIM + 1];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      x[d] = in.x[d][i];
+      ix[d] = in.ix[d][i];
+      seg[0].p0[d] = x[d];
+      seg[0].c[d] = ix[d] - 1 + g.gl[d];  // padded grid coordinate of the cell
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) u[d] = in.p[d][i];
+    const T q = in.q[i];
+    bool inside = true;  // the interpolation stencil (one more point below for the staggered components) must lie on the grid
+#pragma unroll
+    for (int d = 0; d < DIM; d++) inside &= (seg[0].c[d] + LP - 1 >= 0) && (seg[0].c[d] + LP + ORDER < g.S[d]);
+    if (!inside) { atomicOr(errflag, ERRF_BAD_CELL); continue; }
+    T vz = T(0);
+    const T en = push_move_grid<DIM, ORDER, T>(x, u, seg[0].c, f.eb, sy, sz, k, seg[0].p1, di, &vz);
+    if (DIM == 2) seg[0].vz = vz;
+    atomicAdd(ene, (double)(q * en));
+    const int nseg = split_trajectory<DIM, T>(seg, di);
+#pragma unroll 1
+    for (int sidx = 0; sidx < nseg; sidx++) {
+      Seg<DIM, T> sg = seg[0];
+#pragma unroll
+      for (int m = 1; m <= DIM; m++)
+        if (sidx == m) sg = seg[m];
+      int b[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < DIM; d++) b[d] = sg.c[d] + LP;
+      segment_current<DIM, ORDER, T>(sg, q, k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
+        const int q0 = b[0] + k1, q1 = b[1] + k2, q2 = b[2] + k3;
+        if (q0 >= 0 && q0 < g.S[0] && q1 >= 0 && q1 < g.S[1] && q2 >= 0 && q2 < g.S[2]) atomicAdd(&f.j[comp][g.at(q0, q1, q2)], f1 * f2);
+        else atomicOr(errflag, ERRF_BAD_CELL);
+      });
+    }
+    const int m = atomicAdd(out.count, 1);
+    if (m >= out.cap) { atomicOr(errflag, ERRF_MOVER_OVERFLOW); continue; }
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      out.x[d][m] = x[d];
+      out.ix[d][m] = ix[d] + di[d];
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) out.p[d][m] = u[d];
+    out.q[m] = q;
+    if (out.tag) out.tag[m] = in.tag ? in.tag[i] : -1;
+  }
+}
+template <typename T>
+int launch_push_list(int dim, int order, const MoverView<T> &in, const MoverView<T> &out, const T *const *eb6, T *const *j3,
+                     const Grid &g, const pic::PushConst<T> &k, double *ene, int *errflag, cudaStream_t st) {
+  SixPlanes<T> f;
+  for (int c = 0; c < 6; c++) f.eb[c] = eb6[c];
+  for (int c = 0; c < 3; c++) f.j[c] = j3[c];
+#define CASE(D, O) \
+  if (dim == D && order == O) push_list_kernel<D, O, T><<<148 * 4, 128, 0, st>>>(in, out, f, g, k, ene, errflag);
+  CASE(2, 1) CASE(2, 2) CASE(2, 3) CASE(2, 4) CASE(3, 1) CASE(3, 2) CASE(3, 3) CASE(3, 4)
+#undef CASE
+  OSGPU_CUDA(cudaGetLastError());
+  return OSGPU_OK;
+}
+template int launch_push_list<float>(int, int, const MoverView<float> &, const MoverView<float> &, const float *const *,
+                                     float *const *, const Grid &, const pic::PushConst<float> &, double *, int *, cudaStream_t);
+template int launch_push_list<double>(int, int, const MoverView<double> &, const MoverView<double> &, const double *const *,
+                                      double *const *, const Grid &, const pic::PushConst<double> &, double *, int *, cudaStream_t);
+
 template <typename T> void push_tile_shape(int dim, int order, int *box, int *jbox, int *smem_bytes) {
 #define CASE(D, O)                                         \
   if (dim == D && order == O) {                            \

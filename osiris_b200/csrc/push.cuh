@@ -53,6 +53,14 @@ template <typename T> struct PushArgs {
   int *errflag;
 };
 
+// push + deposit of the particles of a list (MoverView `in`, any cell the grids cover, guard cells included)
+// straight from / into global memory; the pushed particles are appended to `out` with their new cell index.
+// For the cells a window move left below the box: the reference pushes them once more before its
+// update_boundary removes them (spec/os-species.f03:171-229).  E, B: the grids the particles interpolate.
+template <typename T>
+int launch_push_list(int dim, int order, const MoverView<T> &in, const MoverView<T> &out, const T *const *eb6, T *const *j3,
+                     const Grid &g, const pic::PushConst<T> &k, double *ene, int *errflag, cudaStream_t st);
+
 template <typename T>
 int launch_push_deposit(int dim, int order, const TmaMaps &maps, const PushArgs<T> &a, int nblocks,
                         cudaStream_t st);

@@ -117,6 +117,13 @@ template <typename T> struct Sim final : SimBase {
     int max_range = 0;            // widest tile slot range of the current layout
     MoverView<T> mv;
     void *mvmem = nullptr;
+    // "guests": the particles a window move left below the box at an absorbing wall.  The reference only
+    // lowers ix in move_window_species and removes them in the update_boundary AFTER the next push
+    // (spec/os-species.f03:171-229), so they are pushed once more -- with the guard-cell fields, depositing
+    // into the guard cells -- outside the cell tiles, by the list pusher (push.cu: push_list_kernel)
+    MoverView<T> gv{};
+    void *gvmem = nullptr;
+    bool guests_pending = false;
     double *d_ene = nullptr;
     bool movers_pending = false;
     int up_slot = -1;          // staging area of an upload in flight (species_upload_begin), -1 none
@@ -606,10 +613,12 @@ template <typename T> struct Sim final : SimBase {
     std::vector<int> cnt(tl.ntile);
     if (ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile) != OSGPU_OK) return -1;
     if (ctl_read(h_pin + 8, s.mv.count, sizeof(int)) != OSGPU_OK) return -1;
+    if (s.guests_pending && ctl_read(h_pin + 9, s.gv.count, sizeof(int)) != OSGPU_OK) return -1;
     if (ctl_sync() != OSGPU_OK) return -1;
     long long n = 0;
     for (int c : cnt) n += c;
     if (s.movers_pending) n += h_pin[8];
+    if (s.guests_pending) n += std::min(h_pin[9], s.gv.cap);
     return n;
   }
 
@@ -620,12 +629,14 @@ template <typename T> struct Sim final : SimBase {
     std::vector<int> cnt(tl.ntile);
     OSGPU_TRY(ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile));
     OSGPU_TRY(ctl_read(h_pin + 8, s.mv.count, sizeof(int)));
+    if (s.guests_pending) OSGPU_TRY(ctl_read(h_pin + 9, s.gv.count, sizeof(int)));
     OSGPU_TRY(ctl_sync());
     std::vector<long long> ooff(tl.ntile + 1);
     long long n = 0;
     for (int t = 0; t < tl.ntile; t++) { ooff[t] = n; n += cnt[t]; }
     const long long nmov = s.movers_pending ? h_pin[8] : 0;
-    const long long np = n + nmov;
+    const long long ngst = s.guests_pending ? std::min(h_pin[9], s.gv.cap) : 0;  // (still below the box: ix < 1)
+    const long long np = n + nmov + ngst;
     if (np == 0) return OSGPU_OK;
     const size_t bix = sizeof(int) * dim * np, bx = sizeof(T) * dim * np, bp = sizeof(T) * 3 * np, bq = sizeof(T) * np;
     const size_t btag = tag ? sizeof(long long) * np : 0, boff = sizeof(long long) * (tl.ntile + 1);
@@ -645,6 +656,7 @@ template <typename T> struct Sim final : SimBase {
       if ((rc = ctl_write(doff, ooff.data(), boff)) != OSGPU_OK) break;
       if ((rc = gather_download<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, doff, g, tl, oix, ox, op, oq, otag, by_tag, st, &launches)) != OSGPU_OK) break;
       if (nmov && (rc = movers_download<T>(s.mv, n, g, oix, ox, op, oq, otag, by_tag, st, &launches)) != OSGPU_OK) break;
+      if (ngst && (rc = movers_download<T>(s.gv, n + nmov, g, oix, ox, op, oq, otag, by_tag, st, &launches)) != OSGPU_OK) break;
       if (cudaMemcpyAsync(ix, oix, bix, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaMemcpyAsync(x, ox, bx, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaMemcpyAsync(p, op, bp, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -695,8 +707,12 @@ template <typename T> struct Sim final : SimBase {
       std::vector<long long> ooff(tl.ntile + 1);
       long long np = 0;
       for (int t = 0; t < tl.ntile; t++) { ooff[t] = np; np += cnt[t]; }
+      unsigned defer = 0;  // axes the window moved along: their lower absorbing wall acts one push later
+      for (int d = 0; d < dim; d++)
+        if (nm[d] > 0) defer |= 1u << d;
+      if (s.guests_pending) { set_error("move_window: species %d was not pushed since the last move", (int)i); return OSGPU_ERR_INVALID; }
       if (np == 0) {  // (still collective across ranks)
-        OSGPU_TRY(species_update_boundary((int)i));
+        OSGPU_TRY(species_boundary((int)i, true, defer));
         continue;
       }
       const size_t bix = sizeof(int) * dim * np, bx_ = sizeof(T) * dim * np, bp = sizeof(T) * 3 * np, bq = sizeof(T) * np;
@@ -716,7 +732,7 @@ template <typename T> struct Sim final : SimBase {
       OSGPU_TRY(gather_download<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, doff, g, tl, oix, ox, op, oq, otag, 0, st, &launches));
       AosParticles<T> in{oix, ox, op, oq, otag};
       OSGPU_TRY(sort_from_staging(s, in, np, sh, true));
-      OSGPU_TRY(species_update_boundary((int)i));
+      OSGPU_TRY(species_boundary((int)i, true, defer));
     }
     return OSGPU_OK;
   }
@@ -767,6 +783,7 @@ template <typename T> struct Sim final : SimBase {
   int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) override {
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
+    if (s.guests_pending) { set_error("species %d: a window move is waiting for its push; use osgpu_species_download", id); return OSGPU_ERR_INVALID; }
     std::vector<int> cnt(tl.ntile);
     OSGPU_TRY(ctl_read(cnt.data(), s.tile_cnt, sizeof(int) * tl.ntile));
     OSGPU_TRY(ctl_read(h_pin + 8, s.mv.count, sizeof(int)));
@@ -1130,6 +1147,16 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaEventRecord(ev[9], st));
     push_events++;
     launches += 1;
+    if (s.guests_pending) {
+      if (accel.on) { set_error("species %d: the beam-initialisation pusher cannot take the guests of a window move", id); return OSGPU_ERR_INVALID; }
+      const Field3<T> &ei = emf_smooth_on ? Ep : E, &bi = emf_smooth_on ? Bp : B;
+      const T *eb6[6] = {ei.c[0], ei.c[1], ei.c[2], bi.c[0], bi.c[1], bi.c[2]};
+      T *j3[3] = {J.c[0], J.c[1], J.c[2]};
+      OSGPU_TRY(launch_push_list<T>(dim, order, s.gv, s.mv, eb6, j3, g, a.k, s.d_ene, d_err, st));
+      OSGPU_CUDA(cudaMemsetAsync(s.gv.count, 0, sizeof(int), st));
+      launches += 1;
+      s.guests_pending = false;
+    }
     s.movers_pending = true;
     return OSGPU_OK;
   }
@@ -1194,6 +1221,7 @@ template <typename T> struct Sim final : SimBase {
   // migrated), or a physical wall with the species boundary condition of the config
   PartBc part_bc() const {
     PartBc bc;
+    bc.defer_lower = 0;
     for (int d = 0; d < 3; d++)
       for (int sd = 0; sd < 2; sd++) {
         const int nb = (d < dim) ? neigh[2 * d + sd] : cfg.rank;
@@ -1205,10 +1233,28 @@ template <typename T> struct Sim final : SimBase {
     return bc;
   }
 
+  int guests_alloc(Species &s) {
+    if (s.gvmem) return OSGPU_OK;
+    const long long np_max = s.cap - 32ll * tl.ntile;
+    const int cap = (int)std::min<long long>(std::max<long long>(65536, np_max / 8), s.mv.cap);
+    const size_t per = (dim + 4) * sizeof(T) + dim * sizeof(int) + sizeof(long long);
+    OSGPU_CUDA(cudaMalloc(&s.gvmem, per * cap + sizeof(int) * 4));
+    char *p = (char *)s.gvmem;
+    s.gv.tag = cfg.no_tags ? nullptr : (long long *)p; p += sizeof(long long) * cap;
+    for (int d = 0; d < 3; d++) { s.gv.x[d] = nullptr; if (d < dim) { s.gv.x[d] = (T *)p; p += sizeof(T) * cap; } }
+    for (int d = 0; d < 3; d++) { s.gv.p[d] = (T *)p; p += sizeof(T) * cap; }
+    s.gv.q = (T *)p; p += sizeof(T) * cap;
+    for (int d = 0; d < 3; d++) { s.gv.ix[d] = nullptr; if (d < dim) { s.gv.ix[d] = (int *)p; p += sizeof(int) * cap; } }
+    s.gv.a = s.gv.b = nullptr;
+    s.gv.count = (int *)p;
+    s.gv.cap = cap;
+    OSGPU_CUDA(cudaMemsetAsync(s.gv.count, 0, sizeof(int) * 4, st));
+    return OSGPU_OK;
+  }
   int species_update_boundary(int id) override { return species_boundary(id, true); }
   // update_boundary_species (spec/os-spec-boundary.f03:1099-1232).  with_migration = false keeps the
   // call local to this rank (no collective): the movers are known to lie inside 1..nx (injection).
-  int species_boundary(int id, bool with_migration) {
+  int species_boundary(int id, bool with_migration, unsigned defer_lower = 0) {
     if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
     Species &s = sp[id];
     if (!s.movers_pending) {
@@ -1217,7 +1263,15 @@ template <typename T> struct Sim final : SimBase {
       OSGPU_CUDA(cudaMemsetAsync(s.mv.count, 0, sizeof(int), st));
     }
     if (multi && with_migration) OSGPU_TRY(migrate(s));
-    OSGPU_TRY(movers_route<T>(s.mv, g, tl, part_bc(), s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, st, &launches));
+    PartBc bc = part_bc();
+    bc.defer_lower = 0;
+    for (int d = 0; d < dim; d++)
+      if (((defer_lower >> d) & 1u) && bc.t[0][d] == PBC_ABSORB) bc.defer_lower |= 1u << d;
+    if (bc.defer_lower) {
+      OSGPU_TRY(guests_alloc(s));
+      s.guests_pending = true;
+    }
+    OSGPU_TRY(movers_route<T>(s.mv, g, tl, bc, s.tile_off[s.cur], s.tile_cnt, s.tile_arr, d_err, s.gv, st, &launches));
     OSGPU_TRY(ctl_read(h_pin, d_err, sizeof(int)));
     OSGPU_TRY(ctl_sync());
     const int f = h_pin[0];
@@ -1372,6 +1426,8 @@ template <typename T> struct Sim final : SimBase {
     for (auto &s : sp) {
       if (s.dl_stage) cudaFree(s.dl_stage);
       if (s.cell_cur) cudaFree(s.cell_cur);
+      if (s.gvmem) cudaFree(s.gvmem);
+      s.gvmem = nullptr;
       s.dl_stage = nullptr; s.dl_cap = 0; s.cell_cur = nullptr;
       for (int k = 0; k < 2; k++) { cudaFree(s.mem[k]); cudaFree(s.tile_off[k]); }
       cudaFree(s.tile_cnt); cudaFree(s.tile_arr); cudaFree(s.mvmem); cudaFree(s.d_ene);

@@ -273,6 +273,68 @@ PIC_HD T push_move(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, T *x1
   return ene;
 }
 
+// The same particle statement with the fields read straight from the grids in global memory (runtime row /
+// plane pitch): for the few particles that are pushed outside the cell tiles -- the cells a window move left
+// below the box (push.cu: push_list_kernel).  c[] = padded grid coordinates of the particle's cell; fused
+// multiply-adds exactly where push_move's scalar nest has them.
+template <int DIM, int ORDER, typename T>
+PIC_HD T push_move_grid(T *x, T *u, const int *c, const T *const *eb6, long long sy, long long sz, const PushConst<T> &k,
+                        T *x1, int *di, T *vz) {
+  constexpr int NP = Stencil<ORDER>::NP, LP = Stencil<ORDER>::LP;
+  T w[DIM][NP], wh[DIM][NP];
+  int b0[DIM], bh[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    spline<ORDER, T>(x[d], w[d]);
+    const bool neg = x[d] < T(0.0);
+    splineh<ORDER, T>(x[d], neg ? T(1.0) : T(0.0), wh[d]);
+    b0[d] = c[d] + LP;
+    bh[d] = c[d] + LP - (neg ? 1 : 0);
+  }
+  T f[6];
+#pragma unroll
+  for (int comp = 0; comp < 6; comp++) {
+    bool hx, hy, hz;
+    if (DIM == 2) {  // E1 (h,.) E2 (.,h) E3 (.,.)  B1 (.,h) B2 (h,.) B3 (h,h)
+      hx = (comp == 0) || (comp == 4) || (comp == 5);
+      hy = (comp == 1) || (comp == 3) || (comp == 5);
+      hz = false;
+    } else {         // E1 (h,.,.) E2 (.,h,.) E3 (.,.,h)  B1 (.,h,h) B2 (h,.,h) B3 (h,h,.)
+      hx = (comp == 0) || (comp == 4) || (comp == 5);
+      hy = (comp == 1) || (comp == 3) || (comp == 5);
+      hz = (comp == 2) || (comp == 3) || (comp == 4);
+    }
+    const T *wx = hx ? wh[0] : w[0], *wy = hy ? wh[1] : w[1], *wz = hz ? wh[DIM - 1] : w[DIM - 1];
+    const T *p = eb6[comp] + (hx ? bh[0] : b0[0]) + sy * (hy ? bh[1] : b0[1]) +
+                 (DIM == 3 ? sz * (hz ? bh[DIM - 1] : b0[DIM - 1]) : 0);
+    T acc = T(0.0);
+#pragma unroll
+    for (int k3 = 0; k3 < (DIM == 3 ? NP : 1); k3++) {
+      T plane = T(0.0);
+#pragma unroll
+      for (int k2 = 0; k2 < NP; k2++) {
+        T line = T(0.0);
+#pragma unroll
+        for (int k1 = 0; k1 < NP; k1++) line = fmadd(p[k1 + sy * k2 + sz * k3], wx[k1], line);
+        plane = fmadd(line, wy[k2], plane);
+      }
+      if (DIM == 3) acc = fmadd(plane, wz[k3], acc);
+      else acc = plane;
+    }
+    f[comp] = acc;
+  }
+  const T ene = boris<T>(k.tem, f[0], f[1], f[2], f[3], f[4], f[5], u);
+  const T rg = rgamma<T>(u);
+#pragma unroll
+  for (int d = 0; d < DIM; d++) {
+    x1[d] = fmadd(u[d] * rg, k.dt_dx[d], x[d]);
+    di[d] = ntrim<T>(x1[d]);
+    x[d] = x1[d] - T(di[d]);
+  }
+  if constexpr (DIM == 2) *vz = u[2] * rg;
+  return ene;
+}
+
 // One particle of accelerate_deposit_{2d,3d} (spec/os-spec-accel.f90:230-397): x1 advances by
 // vdt_dx1 = u_accel dt/dx1 / sqrt(1 + u_accel^2), the other coordinates and the momentum stay; the
 // deposit sees no transverse motion (dxi(2:3) = 0, rg = 0 cancels the 2D out-of-plane current).

@@ -155,7 +155,7 @@ def _window_worker(rank, world, nccl_id, dim, prec, node_dims, gnx, nsteps, out_
     bc = (["absorbing"] * dim, ["specular"] * dim)
     dt = _window_dt(dim)
     sim = Simulation(dim, 2, nxl, [0.5] * dim, dt, precision=prec, node_conf=no_co, nccl_id=nccl_id, device=rank,
-                     part_bc=bc)
+                     part_bc=bc, if_move=[True] + [False] * (dim - 1))
     off = [no_co.coords[d] * nxl[d] for d in range(dim)]
     ppc = 2 ** dim
     part = lattice_species(nxl, [2] * dim, dt_, uth=(0.2, 0.2, 0.2), global_nx=gnx, offset=off)
@@ -197,7 +197,8 @@ def test_moving_window_across_ranks(built, tmp_path, dim, node_dims, fill):
     periodic = [False] + [True] * (dim - 1)
     bc = (["absorbing"] * dim, ["specular"] * dim)
     dt = _window_dt(dim)
-    sim = Simulation(dim, 2, gnx, [0.5] * dim, dt, precision=prec, node_conf=NodeConf(dim, None, periodic, 0), part_bc=bc)
+    sim = Simulation(dim, 2, gnx, [0.5] * dim, dt, precision=prec, node_conf=NodeConf(dim, None, periodic, 0), part_bc=bc,
+                     if_move=[True] + [False] * (dim - 1))
     ppc = 2 ** dim
     part = lattice_species(gnx, [2] * dim, dt_, uth=(0.2, 0.2, 0.2))
     tags0 = _global_tags(part, [0] * dim, gnx, ppc)

@@ -49,6 +49,34 @@ def test_vadvance_deposit_matches_oracle(built, dim, order, prec):
     assert abs(ene - ene_r) <= ETOL[prec] * abs(ene_r)
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_vadvance_deposit_on_branch_inputs(built, dim, order, prec):
+    """the inputs that pin the oracle against the reference's compiled kernels on every branch of the statement
+    (tests/test_oracle_vs_ref.py: particles on cell faces and at +-0, at rest, gamma ~ 100, one / two / three
+    face crossings per step at 0.999 of the Courant limit, outermost cells), through the device: x, p, ix
+    bit for bit"""
+    from osiris_b200.simulation import vadvance_deposit
+    from oracle.bindings import Oracle
+    from test_oracle_vs_ref import _edge_case
+    orc = Oracle(prec)
+    for seed in range(2):
+        c = _edge_case(dim, order, prec, 1000 + 17 * seed + dim + 4 * order)
+        dtmax = 1.0 / np.sqrt(sum(1.0 / h ** 2 for h in DX[dim]))
+        dt = float(c["x"].dtype.type(0.999 * dtmax))
+        ixr, xr, ur, jr = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+        ene_r = orc.advance_deposit(dim, order, ixr, xr, ur, c["q"], -1.0, c["e"], c["b"], c["gc"], jr, c["gc"], DX[dim], dt)
+        ix, x, u, j = c["ix"].copy(), c["x"].copy(), c["u"].copy(), np.zeros_like(c["e"])
+        ene = vadvance_deposit(dim, order, ix, x, u, c["q"], -1.0, c["e"], c["b"], c["gc"], j, c["gc"], DX[dim], dt)
+        assert np.array_equal(ix, ixr), seed
+        assert np.array_equal(x, xr) and np.array_equal(u, ur), seed
+        crossed = (ix != c["ix"]).sum(axis=1)
+        assert (crossed >= 2).any() and (crossed == 0).any()
+        _close_j(j, jr, prec)
+        assert abs(ene - ene_r) <= 10 * ETOL[prec] * abs(ene_r)
+
+
 def test_vadvance_deposit_subrange(built):
     """i0..i1 selects a 1-based inclusive sub-range; everything else is untouched"""
     from osiris_b200.simulation import vadvance_deposit

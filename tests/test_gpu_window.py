@@ -11,12 +11,17 @@ pytestmark = pytest.mark.gpu
 DX = {2: [0.1, 0.12], 3: [0.1, 0.12, 0.09]}
 
 
-def _pair(dim, order, prec, nx, periodic, part_bc, dt, nspecies=1):
+def _pair(dim, order, prec, nx, periodic, part_bc, dt, nspecies=1, if_move=None):
+    """if_move: the axes the window moves along get one more lower guard cell (emf/os-emf.f03:684-688) and the
+    oracle runs the reference's order at the trailing wall: move_window_species only lowers ix, the cells left
+    below the box are pushed once more and removed by the update_boundary after that push
+    (spec/os-species.f03:171-229) -- what the device does with its guest list"""
     from osiris_b200.simulation import NodeConf, Simulation
     no_co = NodeConf(dim, None, periodic, 0)
-    sim = Simulation(dim, order, nx, DX[dim], dt, precision=prec, nspecies=nspecies, node_conf=no_co, part_bc=part_bc)
+    sim = Simulation(dim, order, nx, DX[dim], dt, precision=prec, nspecies=nspecies, node_conf=no_co, part_bc=part_bc,
+                     if_move=if_move)
     ora = OracleSim(dim, order, nx, DX[dim], dt, precision=prec, gc_emf=sim.gc_emf, gc_jay=sim.gc_jay,
-                    periodic=periodic, part_bc=part_bc)
+                    periodic=periodic, part_bc=part_bc, window_order="reference" if if_move else "device")
     return sim, ora
 
 
@@ -63,7 +68,7 @@ def test_moving_window_run_matches_oracle(built, dim, order, prec):
     dt_ = np.float32 if prec == "f32" else np.float64
     periodic = [False] + [True] * (dim - 1)
     bc = (["absorbing"] * dim, ["specular"] * dim)
-    sim, ora = _pair(dim, order, prec, nx, periodic, bc, dt)
+    sim, ora = _pair(dim, order, prec, nx, periodic, bc, dt, if_move=[True] + [False] * (dim - 1))
     c = random_case(dim, order, prec, nx, 4, seed=3, umax=0.15, efield=0.05, gc=sim.gc_emf)
     n0 = c["q"].shape[0]
     tags = np.arange(n0, dtype=np.int64)
@@ -88,6 +93,9 @@ def test_moving_window_run_matches_oracle(built, dim, order, prec):
                 sp.inject(ix, x, p, q, tag=tg)
                 ora.inject(0, ix, x, p, q, tag=tg)
             nmoves += nm
+        if nm > 0:   # between the move and the push the species still holds the cells left below the box
+            assert sp.num_par == ora.species[0]["q"].shape[0], step
+            assert (ora.species[0]["ix"][:, 0] < 1).any()
         sim.iter(1)
         ora.iter(1)
         d = sp.fill_data()

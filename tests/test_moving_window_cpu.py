@@ -97,8 +97,9 @@ def test_space_move_boundary():
 
 
 def test_trailing_wall_deviation_stays_at_the_wall():
-    """the device applies the trailing wall when the window moves, the reference one
-    push later.  The two orders differ only where those last-step particles deposit and re-enter: the
+    """what applying the trailing wall at the window move (round 1) cost against the
+    reference's order (one push later; the device's order since the guest list of round 2).
+    The two orders differ only where those last-step particles deposit and re-enter: the
     first cell columns behind the trailing wall.  The window moves at c, so the difference cannot
     spread into the window: everything a few cells in is identical, step after step."""
     from oracle_sim import OracleSim, random_case

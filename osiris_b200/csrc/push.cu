@@ -33,6 +33,9 @@ namespace osgpu {
 
 using namespace pic;
 
+#ifndef OSGPU_LATE_STAGE
+#define OSGPU_LATE_STAGE 0
+#endif
 #ifndef OSGPU_HALO_JOBS
 #define OSGPU_HALO_JOBS 1
 #endif
@@ -778,7 +781,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       }
       if (s_next[0] < a.tl.ntile) {
         stage_fields(s_next[0]);
+#if !OSGPU_LATE_STAGE
         if (P::FAST) stage_particles(s_next_off, min(s_next[1], P::TCAP));
+#endif
       }
     }
 
@@ -793,10 +798,11 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       if (tid == 0) pre_last = g_cs[G::NCELL];
     }
     // The warps take runs of PB * 32 particles from a counter (a warp that finished its deposit
-    // early sorts more); PB particles per thread in flight: the scratch range sits in L2, latency
-    // is what costs.
+    // early sorts more).  One particle per thread in flight: the scratch range sits in L2 and latency is
+    // what costs, but two per thread spill the loaded values (12.57 -> 12.22 ms per step with one,
+    // profiles/r2_notes.md).
 #ifndef SORT_PB
-#define SORT_PB 2
+#define SORT_PB 1
 #endif
     constexpr int PB = SORT_PB;
     const T *scr0 = a.scc.base + (so >> 5) * P::CHUNK_WORDS + lane;
@@ -861,6 +867,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     }
     if (P::TMA_J && last) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();  // sort done (offsets in hist free), every warp's deposit done, J tile read by the TMA
+#if OSGPU_LATE_STAGE
+    if (P::FAST && tid == 32 && s_next[0] < a.tl.ntile) stage_particles(s_next_off, min(s_next[1], P::TCAP));
+#endif
     if constexpr (!P::TMA_J) {
       for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) {
         const T v = jt[i];

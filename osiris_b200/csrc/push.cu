@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     }
   }
   uint32_t phase = 0, pph = 0;  // mbarrier parities: E/B tile, staged rounds (one bit each)
-  double ene = 0.0;
   T ene_t = T(0);  // per-tile partial in particle precision (the reference sums a chunk in REAL)
+  if (lane == 0) s_ene[wid] = 0.0;
   int cur = 0;  // which of the two cell-offset arrays holds the current tile's
   __syncthreads();
   if (P::FAST && s_tile < a.tl.ntile && s_ns > 0) {
@@ -558,7 +558,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             int ncell = 0;
 #pragma unroll
             for (int d = 0; d < DIM; d++) {
-              moved |= (l[d] < 0) || (l[d] >= tlim[d]);
+              moved |= (unsigned)l[d] >= (unsigned)tlim[d];
               ncell |= (l[d] + 1) << (d * CELL_BITS);
               cross |= di[d] != 0;
             }
@@ -752,8 +752,13 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         }
       } while (more);
     }
-    ene += (double)ene_t;
-    ene_t = T(0);
+    {  // this warp's share of the tile's energy sum: to its double in shared memory
+      T e = ene_t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+      if (lane == 0) s_ene[wid] += (double)e;
+      ene_t = T(0);
+    }
 
     // ---- 4. the last warp to finish its deposit sends the J tile to HBM and starts the next
     // tile's loads; nobody waits: the other warps are already sorting ---------------------------
@@ -907,10 +912,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     cur ^= 1;
   }
 
-  // ---- energy: warp shuffle, then one atomic per CTA ----------------------------------------
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ene += __shfl_down_sync(0xffffffffu, ene, o);
-  if (lane == 0) s_ene[wid] = ene;
+  // ---- energy: one atomic per CTA -----------------------------------------------------------
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;

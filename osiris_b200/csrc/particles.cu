@@ -483,6 +483,134 @@ int deposit_charge(const SpeciesView<T> &sp, const int *tile_off, const int *til
 #undef CASE
   LAUNCHED(1);
 }
+// ---------------------------------------------------------------------------------------------
+// phasespaces (a diagnostic): one CTA per tile, one thread per particle, global atomics.  Arithmetic in
+// the reference's precisions: axis values and weights in p_diag_prec (float), the cell index from the
+// particle-precision product (x - xmin) * rdx (deposit_1D / _2D, os-spec-phasespace.f03:1633-1775).
+// ---------------------------------------------------------------------------------------------
+struct PhaseArgs {
+  osgpu_phasespace ps;
+  double rqm;
+  float dx[3];
+};
+// get_position (spec/os-spec-define.f03:1098-1123): xmin + dx * real((ix + ixmin) + x, p_single)
+template <typename T>
+__device__ __forceinline__ float phase_position(const PhaseArgs &a, int c, const int *ix, const T *x) {
+  return (float)a.ps.xmin[c] + a.dx[c] * (float)((T)(ix[c] + a.ps.ixmin[c]) + x[c]);
+}
+// get_l (os-spec-phasespace.f03:314-409): angular momentum component c about the centre of the global box;
+// in 2D the terms of the absent x3 drop out, exactly as the reference's select case does
+template <int DIM, typename T>
+__device__ __forceinline__ float phase_l(const PhaseArgs &a, int c, const int *ix, const T *x, const T *p) {
+  auto arm = [&](int cx, int cp) { return (phase_position<T>(a, cx, ix, x) - (float)a.ps.center[cx]) * (float)p[cp]; };
+  if (c == 0) {
+    float l = arm(1, 2);
+    if (DIM == 3) l = l - arm(2, 1);
+    return l;
+  }
+  if (c == 1) {
+    float l = -arm(0, 2);
+    if (DIM == 3) l = l + arm(2, 0);
+    return l;
+  }
+  return arm(0, 1) - arm(1, 0);
+}
+// get_phasespace_axis_spec (:3196-3238)
+template <int DIM, typename T>
+__device__ __forceinline__ float phase_axis(const PhaseArgs &a, int k, const int *ix, const T *x, const T *p) {
+  const int c = a.ps.xp_dim[k] - 1;
+  switch (a.ps.x_or_p[k]) {
+  case 1: return phase_position<T>(a, c, ix, x);
+  case 2: return (float)p[c];
+  case 3: return sqrtf((float)(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + T(1)));
+  case 4: return log10f(sqrtf((float)(p[0] * p[0] + p[1] * p[1] + p[2] * p[2] + T(1))));
+  case 5: return phase_l<DIM, T>(a, c, ix, x, p);
+  default: {  // log_ke, never below tiny(1.0_p_single)
+    const T u2 = (p[0] * p[0] + p[1] * p[1]) + p[2] * p[2];
+    return log10f(fmaxf((float)(u2 / (sqrt(T(1) + u2) + T(1))), 1.17549435e-38f));
+  }
+  }
+}
+// get_phasespace_charge (:2627-2737); rqm is a particle-precision number in the reference
+template <typename T>
+__device__ __forceinline__ float phase_quantity(const PhaseArgs &a, T q, const T *p) {
+  const float u2 = (float)(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const float gamma = sqrtf(u2 + 1.0f);
+  const T rqm = (T)a.rqm;
+  const int pt = a.ps.ps_type;
+  float lq;
+  if (pt == 0) lq = (float)q;
+  else if (pt == 1) lq = (float)(rqm * q);
+  else if (pt == 2) lq = (float)(rqm * q) * u2 / (gamma + 1.0f);
+  else if (pt <= 5) lq = ((float)(rqm * q) * u2 / (gamma + 1.0f)) * (float)p[pt - 3] / gamma;
+  else if (pt == 6) lq = fabsf((float)q);
+  else lq = (float)(q * p[pt - 7]) / gamma;
+  if (a.ps.use_ene_bin) {
+    const float kin = u2 / (gamma + 1.0f);
+    if (kin <= (float)a.ps.ene_bin[0] || kin > (float)a.ps.ene_bin[1]) lq = 0.0f;
+  }
+  return lq;
+}
+template <int DIM, typename T>
+__global__ void __launch_bounds__(256)
+    phasespace_kernel(SpeciesView<T> sp, const int *tile_off, const int *tile_cnt, Tiling tl, PhaseArgs a, float *buf) {
+  const int tile = blockIdx.x;
+  const int n = tile_cnt[tile];
+  const long long off = tile_off[tile];
+  int t = tile, o0[3];
+  o0[0] = (t % tl.nt[0]) * tl.T[0]; t /= tl.nt[0];
+  o0[1] = (t % tl.nt[1]) * tl.T[1]; t /= tl.nt[1];
+  o0[2] = t * tl.T[2];
+  const int nd = a.ps.ndims;
+  T rdx[2] = {T(0), T(0)};
+  for (int k = 0; k < nd; k++) rdx[k] = (T)a.ps.n[k] / ((T)a.ps.max[k] - (T)a.ps.min[k]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long s = off + i;
+    const int cell = sp.cell[s];
+    int ix[3] = {1, 1, 1};
+    T x[3] = {T(0), T(0), T(0)}, p[3];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) { ix[d] = o0[d] + cell_l(cell, d) + 1; x[d] = sp.r(d, s); }
+#pragma unroll
+    for (int d = 0; d < 3; d++) p[d] = sp.r(DIM + d, s);
+    const float lq = phase_quantity<T>(a, sp.r(DIM + 3, s), p);
+    // deposit_1D / deposit_2D (:1633-1775): nearest point and the one above it, linear weights
+    int i1[2] = {1, 1};
+    float eps[2] = {0.0f, 0.0f};
+    for (int k = 0; k < nd; k++) {
+      const T nx1 = ((T)phase_axis<DIM, T>(a, k, ix, x, p) - (T)a.ps.min[k]) * rdx[k];
+      i1[k] = (int)lrint(round((double)nx1));  // nint: halves away from zero
+      eps[k] = (float)(nx1 - (T)i1[k]) + 0.5f;
+    }
+    const int n1 = a.ps.n[0];
+    if (nd == 1) {
+      if (i1[0] >= 1 && i1[0] <= n1) atomicAdd(&buf[i1[0] - 1], (1.0f - eps[0]) * lq);
+      if (i1[0] + 1 >= 1 && i1[0] + 1 <= n1) atomicAdd(&buf[i1[0]], eps[0] * lq);
+    } else {
+      for (int b2 = 0; b2 < 2; b2++) {
+        const int j2 = i1[1] + b2;
+        if (j2 < 1 || j2 > a.ps.n[1]) continue;
+        const float w2 = b2 ? eps[1] : 1.0f - eps[1];
+        float *row = buf + (long long)(j2 - 1) * n1;
+        if (i1[0] >= 1 && i1[0] <= n1) atomicAdd(&row[i1[0] - 1], ((1.0f - eps[0]) * w2) * lq);
+        if (i1[0] + 1 >= 1 && i1[0] + 1 <= n1) atomicAdd(&row[i1[0]], (eps[0] * w2) * lq);
+      }
+    }
+  }
+}
+template <typename T>
+int deposit_phasespace(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const Grid &g, const Tiling &tl,
+                       const osgpu_phasespace &ps, double rqm, const double *dx, float *buf, cudaStream_t st,
+                       long long *launches) {
+  PhaseArgs a;
+  a.ps = ps;
+  a.rqm = rqm;
+  for (int d = 0; d < 3; d++) a.dx[d] = (d < g.dim) ? (float)dx[d] : 0.0f;
+  if (g.dim == 2) phasespace_kernel<2, T><<<tl.ntile, 256, 0, st>>>(sp, tile_off, tile_cnt, tl, a, buf);
+  else phasespace_kernel<3, T><<<tl.ntile, 256, 0, st>>>(sp, tile_off, tile_cnt, tl, a, buf);
+  LAUNCHED(1);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) plane_out_kernel(const T *plane, Grid g, T *out, int hs0, int hs1, int hs2, int hg0, int hg1, int hg2) {
   const long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -524,7 +652,9 @@ int plane_to_host_layout(const Grid &g, const T *plane, T *out, const int *hs, c
   template int deposit_charge<T>(const SpeciesView<T> &, const int *, const int *, const Grid &, const Tiling &, \
                                  int, T *, cudaStream_t, long long *);                                        \
   template int plane_to_host_layout<T>(const Grid &, const T *, T *, const int *, const int *, cudaStream_t,   \
-                                       long long *);
+                                       long long *);                                                          \
+  template int deposit_phasespace<T>(const SpeciesView<T> &, const int *, const int *, const Grid &, const Tiling &, \
+                                     const osgpu_phasespace &, double, const double *, float *, cudaStream_t, long long *);
 INST(float)
 INST(double)
 

@@ -65,6 +65,12 @@ int relayout(const SpeciesView<T> &src, const int *old_off, const int *tile_cnt,
 template <typename T>
 int deposit_charge(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const Grid &g, const Tiling &tl,
                    int order, T *rho, cudaStream_t st, long long *launches);
+// phasespace deposit of a species (deposit_1D / deposit_2D of spec/diagnostics/os-spec-phasespace.f03) into a
+// device buffer of n[0] * n[1] floats (ADDED); rqm and dx[] of the species' grid
+template <typename T>
+int deposit_phasespace(const SpeciesView<T> &sp, const int *tile_off, const int *tile_cnt, const Grid &g, const Tiling &tl,
+                       const osgpu_phasespace &ps, double rqm, const double *dx, float *buf, cudaStream_t st,
+                       long long *launches);
 // one padded device plane -> host t_vdf layout f(1, S1h, S2h, S3h) staged on the device
 template <typename T>
 int plane_to_host_layout(const Grid &g, const T *plane, T *out, const int *hsize, const int *hgc, cudaStream_t st,

@@ -62,6 +62,7 @@ struct SimBase {
   virtual int species_update_boundary(int id) = 0;
   virtual int species_energy(int id, double *ene) = 0;
   virtual int species_deposit_charge(int id, void *rho, int accumulate) = 0;
+  virtual int species_phasespace(int id, const osgpu_phasespace *ps, float *buffer, int accumulate) = 0;
   virtual int species_download_async(int id, int *ix, void *x, void *p, void *q, long long *tag) = 0;
   virtual int sync_all() = 0;
   virtual int move_window(const int *nmove) = 0;
@@ -1199,6 +1200,41 @@ template <typename T> struct Sim final : SimBase {
     }
     return OSGPU_OK;
   }
+  // The particle loop of save_phasespace_1D / _2D (spec/diagnostics/os-spec-phasespace.f03:970-1169) for the
+  // particles of this rank.  Refused between move_window and the next push while the species holds guests
+  // of the trailing wall (the reference takes its diagnostics before the window moves, os-main.f03).
+  float *ps_buf = nullptr;
+  size_t ps_cap = 0;
+  int species_phasespace(int id, const osgpu_phasespace *ps, float *buffer, int accumulate) override {
+    if (id < 0 || id >= (int)sp.size() || !sp[id].created) { set_error("species %d not created", id); return OSGPU_ERR_INVALID; }
+    Species &s = sp[id];
+    if (s.movers_pending) { set_error("phasespace: species %d has unprocessed leavers (call update_boundary first)", id); return OSGPU_ERR_INVALID; }
+    if (s.guests_pending) { set_error("phasespace: species %d holds window guests between move_window and push", id); return OSGPU_ERR_INVALID; }
+    if (ps->ndims < 1 || ps->ndims > 2) { set_error("phasespace: ndims = %d (1 or 2; 3D phasespaces are not built)", ps->ndims); return OSGPU_ERR_INVALID; }
+    if (ps->ps_type < 0 || ps->ps_type > 9) { set_error("phasespace: ps_type = %d", ps->ps_type); return OSGPU_ERR_INVALID; }
+    size_t cells = 1;
+    for (int k = 0; k < ps->ndims; k++) {
+      const int kind = ps->x_or_p[k], c = ps->xp_dim[k];
+      if (kind < 1 || kind > 6) { set_error("phasespace: axis %d quantity %d", k, kind); return OSGPU_ERR_INVALID; }
+      if (kind == 1 && (c < 1 || c > dim)) { set_error("phasespace: axis %d is x%d in %dD", k, c, dim); return OSGPU_ERR_INVALID; }
+      if ((kind == 2 || kind == 5) && (c < 1 || c > 3)) { set_error("phasespace: axis %d component %d", k, c); return OSGPU_ERR_INVALID; }
+      if (ps->n[k] < 1 || !(ps->max[k] > ps->min[k])) { set_error("phasespace: axis %d has n = %d, range [%g, %g]", k, ps->n[k], ps->min[k], ps->max[k]); return OSGPU_ERR_INVALID; }
+      cells *= (size_t)ps->n[k];
+    }
+    if (cells > ps_cap) {
+      if (ps_buf) OSGPU_CUDA(cudaFree(ps_buf));
+      ps_buf = nullptr; ps_cap = 0;
+      OSGPU_CUDA(cudaMalloc(&ps_buf, sizeof(float) * cells));
+      ps_cap = cells;
+    }
+    const size_t bytes = sizeof(float) * cells;
+    if (accumulate) OSGPU_CUDA(cudaMemcpyAsync(ps_buf, buffer, bytes, cudaMemcpyHostToDevice, st));
+    else OSGPU_CUDA(cudaMemsetAsync(ps_buf, 0, bytes, st));
+    OSGPU_TRY(deposit_phasespace<T>(s.v[s.cur], s.tile_off[s.cur], s.tile_cnt, g, tl, *ps, s.rqm, cfg.dx, ps_buf, st, &launches));
+    OSGPU_CUDA(cudaMemcpyAsync(buffer, ps_buf, bytes, cudaMemcpyDeviceToHost, st));
+    OSGPU_CUDA(cudaStreamSynchronize(st));
+    return OSGPU_OK;
+  }
   int plane_axpy(T *dst, const T *src) {
     OSGPU_TRY(plane_add<T>(g, dst, src, st, &launches));
     return OSGPU_OK;
@@ -1438,6 +1474,8 @@ template <typename T> struct Sim final : SimBase {
     cudaFree(fld); cudaFree(d_err); cudaFree(d_cnt); cudaFree(d_fe);
     if (stage_mem) cudaFree(stage_mem);
     if (jtmp) cudaFree(jtmp);
+    if (ps_buf) cudaFree(ps_buf);
+    ps_buf = nullptr; ps_cap = 0;
     if (fld_part) cudaFree(fld_part);
     fld_part = nullptr;
     stage_mem = nullptr; stage_cap = 0; jtmp = nullptr;
@@ -1666,6 +1704,11 @@ int osgpu_species_accelerate(osgpu_sim *h, int id, double u_frac, double q_frac,
 int osgpu_species_deposit_charge(osgpu_sim *h, int id, void *rho, int accumulate) {
   H_CHECK(h);
   return h->impl->species_deposit_charge(id, rho, accumulate);
+}
+int osgpu_species_phasespace(osgpu_sim *h, int id, const osgpu_phasespace *ps, float *buffer, int accumulate) {
+  H_CHECK(h);
+  if (!ps || !buffer) { osgpu::set_error("species_phasespace: null argument"); return OSGPU_ERR_INVALID; }
+  return h->impl->species_phasespace(id, ps, buffer, accumulate);
 }
 int osgpu_species_energy(osgpu_sim *h, int id, double *ene) {
   H_CHECK(h);

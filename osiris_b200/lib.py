@@ -34,6 +34,16 @@ class Config(C.Structure):
     ]
 
 
+class Phasespace(C.Structure):
+    """osgpu_phasespace (include/osiris_b200.h)"""
+    _fields_ = [
+        ("ndims", C.c_int32), ("x_or_p", C.c_int32 * 2), ("xp_dim", C.c_int32 * 2), ("ps_type", C.c_int32),
+        ("n", C.c_int32 * 2), ("use_ene_bin", C.c_int32),
+        ("min", C.c_double * 2), ("max", C.c_double * 2), ("ene_bin", C.c_double * 2),
+        ("xmin", C.c_double * 3), ("center", C.c_double * 3), ("ixmin", C.c_int32 * 3),
+    ]
+
+
 TOPO_MPI, TOPO_OLD, TOPO_HOST = 0, 1, 2
 
 
@@ -77,6 +87,7 @@ def load():
     L.osgpu_species_accelerate.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
     L.osgpu_species_energy.argtypes = [vp, C.c_int, dp]
     L.osgpu_species_deposit_charge.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.osgpu_species_phasespace.argtypes = [vp, C.c_int, C.POINTER(Phasespace), vp, C.c_int]
     L.osgpu_current_zero.argtypes = [vp]
     L.osgpu_move_window.argtypes = [vp, vp]
     L.osgpu_species_inject.argtypes = [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp]
@@ -154,5 +165,6 @@ EXPORTS = [
     "osgpu_species_download_async", "osgpu_species_upload_begin", "osgpu_species_upload_end",
     "osgpu_emf_set_smooth", "osgpu_emf_update_particle_fld", "osgpu_move_window", "osgpu_species_inject",
     "osgpu_exchange_ranges_move", "osgpu_vadvance_deposit_release", "osgpu_species_accelerate",
-    "osgpu_species_energy", "osgpu_species_deposit_charge", "osgpu_emf_set_solver", "osgpu_field_wall_op", "osgpu_current_wall_op",
+    "osgpu_species_energy", "osgpu_species_deposit_charge", "osgpu_species_phasespace",
+    "osgpu_emf_set_solver", "osgpu_field_wall_op", "osgpu_current_wall_op",
 ] + [f"osgpu_vadvance_deposit_{d}d_s{o}{s}" for d in (2, 3) for o in (1, 2, 3, 4) for s in ("", "_d")]

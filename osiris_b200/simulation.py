@@ -219,6 +219,39 @@ class Species:
         check(self.sim._L.osgpu_species_deposit_charge(self.sim._h, self.sp_id, ptr(rho), int(accumulate)))
         return rho
 
+    # axis quantities and deposited quantities of a phasespace, by the reference's deck names
+    # (spec/diagnostics/os-spec-phasespace.f03:28-46; "p1x1" = x1 on the first axis, p1 on the second)
+    PHASE_AXIS = {"x": 1, "p": 2, "g": 3, "gl": 4, "l": 5, "kel": 6}
+    PHASE_TYPE = {"charge": 0, "m": 1, "ene": 2, "q1": 3, "q2": 4, "q3": 5, "|charge|": 6, "j1": 7, "j2": 8, "j3": 9}
+
+    def phasespace(self, axes, n, lo, hi, ps_type="charge", ene_bin=None, g_box=None, my_nx_p_lo=None,
+                   buffer=None):
+        """The particle loop of save_phasespace_1D / _2D (os-spec-phasespace.f03:970-1169): deposit this
+        rank's particles of the species on the phasespace grid.  axes: one or two of ("x", 1), ("p", 2),
+        ("g", 0), ("gl", 0), ("l", 3), ("kel", 0), FIRST axis first; n, lo, hi: points and range per axis.
+        g_box ([lower], [upper]) and my_nx_p_lo (global index of this rank's first cell, 1-based) default to
+        a box starting at 0 split evenly over the nodes.  Returns float32 [n2, n1] (or [n1]); buffer, when
+        given, is added to.  The sum over ranks and the normalisation stay with the caller."""
+        sim = self.sim
+        ps = _lib.Phasespace()
+        ps.ndims = len(axes)
+        for k, (kind, comp) in enumerate(axes):
+            ps.x_or_p[k], ps.xp_dim[k] = self.PHASE_AXIS[kind], int(comp)
+            ps.n[k], ps.min[k], ps.max[k] = int(n[k]), float(lo[k]), float(hi[k])
+        ps.ps_type = self.PHASE_TYPE[ps_type]
+        if ene_bin is not None:
+            ps.use_ene_bin, ps.ene_bin[0], ps.ene_bin[1] = 1, float(ene_bin[0]), float(ene_bin[1])
+        for d in range(sim.dim):
+            glo = g_box[0][d] if g_box is not None else 0.0
+            gup = g_box[1][d] if g_box is not None else sim.nx[d] * sim.dx[d] * sim.no_co.node_number[d]
+            first = my_nx_p_lo[d] if my_nx_p_lo is not None else sim.no_co.coords[d] * sim.nx[d] + 1
+            ps.xmin[d], ps.center[d], ps.ixmin[d] = glo, (glo + gup) / 2, int(first) - 2
+        shape = tuple(int(v) for v in reversed(n[:len(axes)]))
+        out = np.zeros(shape, np.float32) if buffer is None else buffer
+        assert out.dtype == np.float32 and out.shape == shape and out.flags.c_contiguous
+        check(sim._L.osgpu_species_phasespace(sim._h, self.sp_id, C.byref(ps), ptr(out), int(buffer is not None)))
+        return out
+
     @property
     def energy(self):
         """this%energy(1) of the last push (sum q u^2/(gamma+1); get_energy multiplies by rqm * cell volume)"""

@@ -196,3 +196,24 @@ def test_exchange_ranges_after_a_window_move():
     r1 = (C.c_int32 * 8)()
     L.osgpu_exchange_ranges_move(nx, gcl, gcu, 0, 0, r1)
     assert list(r0) == list(r1)
+
+
+def test_ctypes_structs_have_the_header_layout(tmp_path):
+    """The ctypes mirrors of osgpu_config and osgpu_phasespace against the C compiler's view of include/osiris_b200.h"""
+    import subprocess
+    from osiris_b200 import lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = {"osgpu_config": [f[0] for f in lib.Config._fields_], "osgpu_phasespace": [f[0] for f in lib.Phasespace._fields_]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "osiris_b200.h"', 'int main(void) {']
+    for st, names in fields.items():
+        src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        src += [f'  printf("{st}.{n} %zu\\n", offsetof({st}, {n}));' for n in names]
+    src += ['  return 0;', '}']
+    (tmp_path / "layout.c").write_text("\n".join(src))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), "-o", exe, str(tmp_path / "layout.c")], check=True)
+    got = dict(line.split() for line in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st, cls in (("osgpu_config", lib.Config), ("osgpu_phasespace", lib.Phasespace)):
+        assert int(got[st]) == C.sizeof(cls), st
+        for n in fields[st]:
+            assert int(got[f"{st}.{n}"]) == getattr(cls, n).offset, (st, n)

@@ -10,6 +10,10 @@ boundary + re-binning -> J guard sum -> Yee) over synthetic particles resident i
 prints ONE JSON line (contract in the round prompt; keys `roofline`, `cpu_baseline`, `e2e`,
 `clocks`, `gpu_launches`).
 
+The particles are loaded on the reference's lattice and advanced --settle steps (default 20, named in
+`config.load`, the same on both arms) before the W warm-up steps: lattice-loaded particles reach their first cell
+faces together in steps 3-8, which cost up to 20 % more than any later step (profiles/r2_steptimes.txt).
+
 Weak scaling: every GPU owns the workload's per-GPU box (3D uniform: 256^3 cells x 8 ppc); ranks
 form a cartesian grid (8 -> 2x2x2) with NCCL guard-cell / migration exchanges inside the library.
 """
@@ -31,6 +35,7 @@ from osiris_b200.loads import WORKLOADS, lattice_species  # noqa: E402
 
 METRIC = "particle-steps/s (push+deposit+solve)"
 UNIT = "particle-steps/s"
+SETTLE_STEPS = 20
 # algorithmic bytes (SURVEY.md 8d / BASELINE.md 2): per particle-step and per cell-step
 B_P = {(2, 4): 60, (3, 4): 76, (2, 8): 104, (3, 8): 128}
 B_C = {4: 96, 8: 192}
@@ -182,8 +187,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=10, help="untimed steps (>= 3); the default also covers the first "
-                    "cell crossings of the lattice-loaded particles, steps 3-8 run up to 20 %% slower (profiles/r2_steptimes.txt)")
+    ap.add_argument("--warmup", type=int, default=5, help="untimed steps (>= 3)")
+    ap.add_argument("--settle", type=int, default=SETTLE_STEPS,
+                    help="steps run while the workload is set up, before the warm-up, on both arms: the particles are "
+                    "loaded on the reference's lattice (inject_std) and cross their first cell faces together in "
+                    "steps 3-8, which run up to 20 %% slower than every later step (profiles/r2_steptimes.txt); the "
+                    "metric is quoted on the thermalised plasma")
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="uniform3d")
     ap.add_argument("--prec", default="f32")
@@ -207,6 +216,7 @@ def main():
                   "ppc": int(np.prod(w["ppc"])), "species": len(w["species"]), "precision": args.prec,
                   "particles_per_gpu": int(np.prod(nx)) * int(np.prod(w["ppc"])) * len(w["species"]),
                   "node_dims": node_dims(N, dim),
+                  "load": f"lattice (inject_std) + thermal momenta, advanced {args.settle} steps before the warm-up",
                   "cache": "inputs larger than L2 (particle buffers >> 126 MB)"}
 
     if args.impl == "reference":
@@ -214,7 +224,7 @@ def main():
             return 0
         # bounded sample of the same workload: 1/8 of the per-GPU volume
         sample = [max(16, n // 2) for n in nx]
-        val, info = cpu_reference_run(w, args.prec, steps, warmup, sample)
+        val, info = cpu_reference_run(w, args.prec, steps, warmup + args.settle, sample)
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": N, "steps": steps,
                 "warmup": warmup, "ms_per_step": 1e3 * info["seconds"] / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.prec, "data": "synthetic",
@@ -264,6 +274,7 @@ def main():
             dist.barrier()
         sim.sync()
 
+    sim.iter(args.settle)
     sim.iter(warmup)
     sampler = ClockSampler(local)
     barrier()
@@ -316,6 +327,10 @@ def main():
 
     # ---- end to end through the C ABI with HOST buffers (N = 1) -----------------------------
     emf_shape = sim.emf_shape
+    if world == 1 and args.e2e_steps > 0:  # the same thermalised particles, back on the host
+        for i, sp in enumerate(sim.species):
+            d = sp.fill_data(sort_by_tag=False)
+            host_parts[i] = {k: d[k] for k in ("ix", "x", "p", "q")}
     sim.close()
     if world == 1 and args.e2e_steps > 0 and rank == 0:
         line["e2e"] = e2e_run(lib, w, nx, host_parts, args.e2e_steps, dt_, args.prec, emf_shape, args.e2e_chunks)
@@ -324,7 +339,7 @@ def main():
         try:
             sample = [max(16, n // 2) for n in nx]
             cs = max(2, min(10, steps))
-            val, info = cpu_reference_run(w, args.prec, cs, 1, sample)
+            val, info = cpu_reference_run(w, args.prec, cs, 1 + args.settle, sample)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                                     "sample": info["sample"]}
         except Exception as ex:  # the checker is optional for the product line, never the reverse

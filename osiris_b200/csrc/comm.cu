@@ -18,6 +18,7 @@ struct Api {
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char *(*GetErrorString)(ncclResult_t);
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *);  // optional (NCCL >= 2.18)
   void *lib = nullptr;
 } api;
 
@@ -48,6 +49,7 @@ int load_api() {
   SYM(GroupEnd, "ncclGroupEnd")
   SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
+  *(void **)(&api.CommSplit) = dlsym(h, "ncclCommSplit");
   api.lib = h;
   return OSGPU_OK;
 }
@@ -82,6 +84,18 @@ int Nccl::init(const void *id128, int nranks_, int rank_) {
   comm = c;
   rank = rank_;
   nranks = nranks_;
+  return OSGPU_OK;
+}
+
+int Nccl::clone(Nccl *out) {
+  *out = Nccl();
+  out->lib = lib;
+  out->rank = rank;
+  out->nranks = nranks;
+  if (!comm || !api.CommSplit) return OSGPU_OK;
+  ncclComm_t c = nullptr;
+  NCCL_TRY(api.CommSplit((ncclComm_t)comm, 0, rank, &c, nullptr));
+  out->comm = c;
   return OSGPU_OK;
 }
 

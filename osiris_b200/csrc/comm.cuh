@@ -19,6 +19,9 @@ struct Nccl {
   int load();                                   // dlopen + resolve; OSGPU_ERR_NCCL on failure
   static int unique_id(void *id128);
   int init(const void *id128, int nranks, int rank);
+  // a second communicator over the same ranks (ncclCommSplit), for exchanges that run on another stream at the
+  // same time as this one's; collective.  out->comm stays null when the loaded libnccl has no ncclCommSplit.
+  int clone(Nccl *out);
   void destroy();
   // one neighbour exchange: send `ns0` bytes to peer `to0` and `ns1` bytes to `to1` while
   // receiving from `from0` / `from1`; a peer of -1 skips that leg.  Sends are posted before

@@ -101,6 +101,14 @@ template <typename T> struct Sim final : SimBase {
   int neigh[6];  // lower/upper neighbour rank per axis, -1 none, == rank: in-rank periodic
   Nccl nccl;
   bool multi = false;
+  // osgpu_step runs the particle boundary (migration, re-layout) on its own stream, with its own communicator,
+  // while the launching stream goes on with the J guard cells, the field solve and the next step's E/B guard
+  // cells: the two touch disjoint data between one push and the next (OSGPU_NO_OVERLAP=1 keeps one stream)
+  Nccl nccl_part;
+  cudaStream_t st_part = nullptr;
+  cudaEvent_t ev_part[2] = {};
+  cudaEvent_t ev_emfb[4] = {};  // E/B guard-cell phase of this step [0,1] and, queued early, of the next [2,3]
+  bool overlap = false;
 
   struct Species {
     bool created = false;
@@ -288,6 +296,9 @@ template <typename T> struct Sim final : SimBase {
     OSGPU_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto &e : ev) OSGPU_CUDA(cudaEventCreate(&e));
     for (auto &e : ev_sm) OSGPU_CUDA(cudaEventCreate(&e));
+    OSGPU_CUDA(cudaStreamCreateWithFlags(&st_part, cudaStreamNonBlocking));
+    for (auto &e : ev_part) OSGPU_CUDA(cudaEventCreate(&e));
+    for (auto &e : ev_emfb) OSGPU_CUDA(cudaEventCreate(&e));
     OSGPU_CUDA(cudaStreamCreateWithFlags(&st_d2h, cudaStreamNonBlocking));
     OSGPU_CUDA(cudaEventCreateWithFlags(&ev_dl, cudaEventDisableTiming));
     OSGPU_CUDA(cudaStreamCreateWithFlags(&st_h2d, cudaStreamNonBlocking));
@@ -351,6 +362,7 @@ template <typename T> struct Sim final : SimBase {
         return OSGPU_ERR_INVALID;
       }
       OSGPU_TRY(nccl.init(nccl_id, c->nranks, c->rank));
+      OSGPU_TRY(nccl.clone(&nccl_part));
       // field exchange buffers: widest slab (gl+gu cells) x largest cross-section x 6 components
       size_t big = 0;
       for (int d = 0; d < dim; d++) {
@@ -361,6 +373,10 @@ template <typename T> struct Sim final : SimBase {
       }
       xbuf_elems = big * 6;
       for (auto &b : xbuf) OSGPU_CUDA(cudaMalloc(&b, xbuf_elems * sizeof(T)));
+    }
+    {
+      const char *no = getenv("OSGPU_NO_OVERLAP");
+      overlap = !(no && no[0] == '1') && (!multi || nccl_part.comm != nullptr);
     }
     sp.resize(std::max(0, (int)c->nspecies));
     OSGPU_TRY(setup_walls());
@@ -1394,47 +1410,77 @@ template <typename T> struct Sim final : SimBase {
   // ---------------------------------------------------------------------------------------
   int step(int nsteps, double *ene) override {
     for (int k = 0; k < 8; k++) phase_ms[k] = 0;
+    auto elapsed = [](cudaEvent_t a, cudaEvent_t b, double *acc) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { set_error("cudaEventElapsedTime: %s", cudaGetErrorString(cudaGetLastError())); return OSGPU_ERR_CUDA; }
+      *acc += ms;
+      return OSGPU_OK;
+    };
     OSGPU_CUDA(cudaEventRecord(ev[6], st));
+    bool guards_queued = false;  // overlap: this step's E/B guard cells went out behind the previous step's solve
     for (int n = 0; n < nsteps; n++) {
       const bool last = (n == nsteps - 1);
-      OSGPU_CUDA(cudaEventRecord(ev[0], st));
-      OSGPU_TRY(emf_update_boundary());
-      OSGPU_TRY(emf_update_particle_fld());
+      if (!guards_queued) {
+        OSGPU_CUDA(cudaEventRecord(ev_emfb[0], st));
+        OSGPU_TRY(emf_update_boundary());
+        OSGPU_TRY(emf_update_particle_fld());
+        OSGPU_CUDA(cudaEventRecord(ev_emfb[1], st));
+      }
+      if (overlap && n > 0) OSGPU_CUDA(cudaStreamWaitEvent(st, ev_part[1], 0));  // the particles of step n - 1 are in place
       OSGPU_CUDA(cudaEventRecord(ev[1], st));
       OSGPU_TRY(advance_deposit(nullptr));
       OSGPU_CUDA(cudaEventRecord(ev[2], st));
-      OSGPU_TRY(particles_update_boundary());  // synchronises (tile-capacity check)
-      if (sp.size() == 1 && sp[0].created) {   // single species: ev[8..9] bracket its one launch
-        float ms = 0;
-        OSGPU_CUDA(cudaEventElapsedTime(&ms, ev[8], ev[9]));
-        phase_ms[6] += ms;
-      }
+      if (!overlap) OSGPU_TRY(particles_update_boundary());  // synchronises (tile-capacity check)
       OSGPU_CUDA(cudaEventRecord(ev[3], st));
       OSGPU_TRY(current_update_boundary());
       OSGPU_TRY(current_smooth());
       OSGPU_CUDA(cudaEventRecord(ev[4], st));
       OSGPU_TRY(emf_advance());
       OSGPU_CUDA(cudaEventRecord(ev[5], st));
-      if (last && ene)
-        for (size_t i = 0; i < sp.size(); i++)
-          if (sp[i].created) OSGPU_CUDA(cudaMemcpyAsync(&ene[i], sp[i].d_ene, sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (overlap) {
+        // The field side above is all queued (nothing in it waits for the host); the next step's E/B guard
+        // cells belong to the same window.  Then the particle boundary, which synchronises ITS stream.
+        cudaEvent_t nb[2] = {ev_emfb[2], ev_emfb[3]};
+        if (!last) {
+          OSGPU_CUDA(cudaEventRecord(nb[0], st));
+          OSGPU_TRY(emf_update_boundary());
+          OSGPU_TRY(emf_update_particle_fld());
+          OSGPU_CUDA(cudaEventRecord(nb[1], st));
+        }
+        OSGPU_CUDA(cudaStreamWaitEvent(st_part, ev[2], 0));
+        std::swap(st, st_part);
+        std::swap(nccl, nccl_part);
+        cudaEventRecord(ev_part[0], st);
+        const int rc = particles_update_boundary();
+        cudaEventRecord(ev_part[1], st);
+        std::swap(st, st_part);
+        std::swap(nccl, nccl_part);
+        if (rc != OSGPU_OK) return rc;
+        OSGPU_CUDA(cudaEventSynchronize(ev_part[1]));
+        OSGPU_TRY(elapsed(ev_part[0], ev_part[1], &phase_ms[2]));
+      }
+      if (last) {
+        if (overlap) OSGPU_CUDA(cudaStreamWaitEvent(st, ev_part[1], 0));  // whatever the host queues next sees the particles
+        if (ene)
+          for (size_t i = 0; i < sp.size(); i++)
+            if (sp[i].created) OSGPU_CUDA(cudaMemcpyAsync(&ene[i], sp[i].d_ene, sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
       OSGPU_CUDA(cudaEventSynchronize(ev[5]));
-      for (int k = 0; k < 5; k++) {
-        float ms = 0;
-        OSGPU_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
-        phase_ms[k] += ms;
-      }
-      if (smooth_on) {  // 'current smooth' (also inside the current-boundary interval)
-        float ms = 0;
-        OSGPU_CUDA(cudaEventElapsedTime(&ms, ev_sm[0], ev_sm[1]));
-        phase_ms[7] += ms;
-      }
+      OSGPU_TRY(elapsed(ev_emfb[0], ev_emfb[1], &phase_ms[0]));
+      OSGPU_TRY(elapsed(ev[1], ev[2], &phase_ms[1]));
+      if (!overlap) OSGPU_TRY(elapsed(ev[2], ev[3], &phase_ms[2]));
+      OSGPU_TRY(elapsed(ev[3], ev[4], &phase_ms[3]));
+      OSGPU_TRY(elapsed(ev[4], ev[5], &phase_ms[4]));
+      if (sp.size() == 1 && sp[0].created) OSGPU_TRY(elapsed(ev[8], ev[9], &phase_ms[6]));  // single species: its one launch
+      if (smooth_on) OSGPU_TRY(elapsed(ev_sm[0], ev_sm[1], &phase_ms[7]));  // 'current smooth' (inside the current-boundary interval)
+      guards_queued = overlap && !last;
+      if (guards_queued) { std::swap(ev_emfb[0], ev_emfb[2]); std::swap(ev_emfb[1], ev_emfb[3]); }  // read after the NEXT solve
     }
     OSGPU_CUDA(cudaEventRecord(ev[7], st));
     OSGPU_CUDA(cudaStreamSynchronize(st));
     float tot = 0;
     OSGPU_CUDA(cudaEventElapsedTime(&tot, ev[6], ev[7]));
-    phase_ms[5] = tot;  // first launch to last completion, gaps included
+    phase_ms[5] = tot;  // first launch to last completion, gaps and cross-stream waits included
     return OSGPU_OK;
   }
 
@@ -1456,6 +1502,7 @@ template <typename T> struct Sim final : SimBase {
 
   int finalize() override {
     if (st) cudaStreamSynchronize(st);
+    if (st_part) cudaStreamSynchronize(st_part);
     if (st_d2h) cudaStreamSynchronize(st_d2h);
     if (st_h2d) cudaStreamSynchronize(st_h2d);
     for (int k = 0; k < 2; k++) { if (up_mem[k]) cudaFree(up_mem[k]); up_mem[k] = nullptr; up_cap[k] = 0; }
@@ -1482,6 +1529,7 @@ template <typename T> struct Sim final : SimBase {
     if (h_pin) cudaFreeHost(h_pin);
     if (h_ctl) cudaFreeHost(h_ctl);
     h_ctl = nullptr; ctl_cap = 0;
+    nccl_part.destroy();
     nccl.destroy();
     auto drop_event = [](cudaEvent_t &e) { if (e) cudaEventDestroy(e); e = nullptr; };
     auto drop_stream = [](cudaStream_t &q) { if (q) cudaStreamDestroy(q); q = nullptr; };
@@ -1490,6 +1538,9 @@ template <typename T> struct Sim final : SimBase {
     for (auto &e : ev_up_done) drop_event(e);
     for (auto &e : ev_up_free) drop_event(e);
     drop_event(ev_dl);
+    for (auto &e : ev_part) drop_event(e);
+    for (auto &e : ev_emfb) drop_event(e);
+    drop_stream(st_part);
     drop_stream(st_d2h);
     drop_stream(st_h2d);
     drop_stream(st);

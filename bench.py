@@ -68,33 +68,45 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.perf_counter()])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples read between t0 and t1 (perf_counter): the timed region.  nvidia-smi needs a few hundred ms to
+        produce its first line, so the sampler is started before the warm-up and the rows are filtered here; a timed
+        region shorter than the sampling period takes the rows of the second before it as well (GPU under the same
+        load: the warm-up steps) and says so in `window`."""
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows, window = list(self.rows), "all"
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[-1] <= t1]
+            window = "timed region"
+            if not inside:
+                inside = [r for r in rows if t0 - 1.0 <= r[-1] <= t1 + 0.05]
+                window = "timed region and the second of warm-up before it"
+            rows = inside
+        sm = [float(r[1]) for r in rows if len(r) >= 10 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
+        for r in rows:
+            if len(r) >= 10:
                 for k, nm in enumerate(names):
                     if r[5 + k].lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def cpu_reference_run(w, prec, steps, warmup, sample_nx, threads=None):
@@ -259,13 +271,14 @@ def main():
     off = [no_co.coords[d] * nx[d] for d in range(dim)]
     dt_ = np.float32 if args.prec == "f32" else np.float64
     npart = 0
-    host_parts = []
+    host_parts, sps = [], []
     for i, s in enumerate(w["species"]):
         part = lattice_species(nx, w["ppc"], dt_, rqm=s["rqm"], uth=s["uth"], ufl=s["ufl"], seed=42 + i,
                                global_nx=gnx, offset=off)
         n = part["q"].shape[0]
         sp = sim.add_species(f"species{i}", s["rqm"], int(n * 1.25) + 65536)
         sp.upload(part["ix"], part["x"], part["p"], part["q"])
+        sps.append(sp)
         npart += n
         host_parts.append(part if (world == 1 and args.e2e_steps > 0) else None)
 
@@ -274,17 +287,18 @@ def main():
             dist.barrier()
         sim.sync()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     sim.iter(args.settle)
     sim.iter(warmup)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     l0 = sim.launch_count
     t0 = time.perf_counter()
     sim.iter(steps)
     barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    t1 = time.perf_counter()
+    wall = t1 - t0
+    clocks = sampler.stop(t0, t1)
     launches = sim.launch_count - l0
     pt = sim.phase_times_ms()
     dev_ms = pt["loop"]  # CUDA events on the launching stream, first launch to last completion
@@ -328,7 +342,7 @@ def main():
     # ---- end to end through the C ABI with HOST buffers (N = 1) -----------------------------
     emf_shape = sim.emf_shape
     if world == 1 and args.e2e_steps > 0:  # the same thermalised particles, back on the host
-        for i, sp in enumerate(sim.species):
+        for i, sp in enumerate(sps):
             d = sp.fill_data(sort_by_tag=False)
             host_parts[i] = {k: d[k] for k in ("ix", "x", "p", "q")}
     sim.close()

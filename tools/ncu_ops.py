@@ -1,8 +1,11 @@
 """Opcode histogram of a kernel in an ncu report (warp instructions executed per opcode, per particle).
-    python tools/ncu_ops.py gpurun_out/prof.ncu-rep <nparticles> [top]"""
+    python tools/ncu_ops.py gpurun_out/prof.ncu-rep <nparticles> [top] [lo_offset hi_offset]
+lo/hi: byte offsets from the kernel's first instruction (the region ends tools/ncu_regions.py prints), hex."""
 import collections, csv, subprocess, sys
 rep, npart = sys.argv[1], float(sys.argv[2])
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+lo, hi = (int(sys.argv[4], 16), int(sys.argv[5], 16)) if len(sys.argv) > 5 else (0, 1 << 60)
+base = None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr = None
@@ -11,6 +14,8 @@ for r in rows:
     if r and r[0] == "Address": hdr = r; continue
     if hdr is None or not r or not r[0].startswith("0x"): continue
     d = dict(zip(hdr, r))
+    if base is None: base = int(r[0], 16)
+    if not (lo < int(r[0], 16) - base <= hi): continue
     s = d["Source"].strip()
     parts = s.split()
     op = parts[1] if parts[0].startswith("@") else parts[0]

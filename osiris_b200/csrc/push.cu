@@ -36,6 +36,12 @@ using namespace pic;
 #ifndef OSGPU_LATE_STAGE
 #define OSGPU_LATE_STAGE 0
 #endif
+// the per-cell walk of the deposit as a lambda (1) or expanded in place (0), per dimensionality: the
+// same statements, different register allocation -- measured per case (profiles/r2_notes.md)
+// (same box: 2D linear 2.32 -> 2.19 ms and 3D cubic 7.44 -> 7.16 ms as a lambda, 3D quadratic 12.19 -> 12.22)
+#ifndef OSGPU_WALK_LAMBDA_FOR
+#define OSGPU_WALK_LAMBDA_FOR(DIM, ORDER) ((DIM) == 2 || (ORDER) == 3)
+#endif
 #ifndef OSGPU_HALO_JOBS
 #define OSGPU_HALO_JOBS 1
 #endif
@@ -133,10 +139,13 @@ __device__ __forceinline__ int block_scan(int v, int *total, int *s_warp) {
 // shared-memory plan of one instantiation
 template <int DIM, int ORDER, typename T> struct Plan {
   using G = Tile<DIM, ORDER, T>;
-  // orders 1-2: the particles of a tile are staged in shared memory by TMA bulk copies and the
+  // orders 1-3: the particles of a tile are staged in shared memory by TMA bulk copies and the
   // in-cell piece of every sorted particle is accumulated in registers per cell (12 / 54 values in
-  // 3D); orders 3-4 would need 144 / 300 registers: they load from global memory and deposit directly
-  static constexpr bool FAST = ORDER <= 2;
+  // 3D; the 144 of the 3D cubic scheme one current component -- 48 values -- per pass over the cell's
+  // trajectories); order 4 would need 100 registers per component: it loads from global memory and
+  // deposits directly
+  static constexpr bool FAST = ORDER <= 3;
+  static constexpr int NPASS = (ORDER == 3 && (DIM == 3 || sizeof(T) == 8)) ? 3 : 1;  // (2D cubic fp64: 40 sums = 80 registers)
   static constexpr int NWARP = NTHREADS / 32;
   static constexpr int NC = DIM + 4;            // staged columns: x(D) u(3) q, blocked by 32 slots
   static constexpr int CHUNK_WORDS = NC * 32;   // one block of 32 slots
@@ -147,7 +156,11 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // momentum slots hold the end point of the trajectory), above them one region per warp with the
   // list of pieces that belong to other cells of the tile and the queue of particles to split, and
   // at the top the CTA's list of pieces that lie in halo cells
-  static constexpr int BUF_BYTES = FAST ? 74752 - (OSGPU_PAD_EY && DIM == 3 && ORDER == 2 && sizeof(T) == 4 ? 2304 : 0) : 0;  // (2 CTAs per SM: the padded 3D quadratic E/B tile takes 2304 B more)
+  // (2 CTAs per SM: the padded 3D quadratic E/B tile takes 2304 B more; the 3D cubic fp32 tiles -- 27 KB of
+  // E/B, 22 KB of J -- leave room for 1824 staged particles, so a tile of 2048 + arrivals takes two pieces)
+  static constexpr int BUF_BYTES = !FAST ? 0
+      : (DIM == 3 && ORDER == 3 && sizeof(T) == 4) ? 60672
+      : 74752 - (OSGPU_PAD_EY && DIM == 3 && ORDER == 2 && sizeof(T) == 4 ? 2304 : 0);
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
   static constexpr int XMIN = 20;  // list entries per warp always available
   static constexpr int HCAP = OSGPU_PAD_EY ? 64 : 96;  // CTA-wide list of pieces in halo cells (top of the buffer)
@@ -155,7 +168,7 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr int NROUND = FAST ? (TCAP + NTHREADS - 1) / NTHREADS : 1;
   static_assert(NROUND <= 16, "one mbarrier (and one phase bit) per staged round");
   static_assert(!FAST || TCAP < 4096, "queue entries keep the slot in 12 bits");
-  static constexpr int NACC = 3 * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
+  static constexpr int NACC = (NPASS == 1 ? 3 : 1) * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
   static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
   static constexpr int OFF_BUF = round_up(OFF_JT + 3 * G::JVOL * (int)sizeof(T), 128);
   static constexpr int OFF_CS = OFF_BUF + BUF_BYTES;
@@ -168,8 +181,8 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // all instantiations but 3D fp64 are meant to run two CTAs per SM: 233472 bytes per SM, 1024 reserved
   // per CTA, < 512 bytes of static shared variables in the kernel
   static_assert((sizeof(T) == 8 && DIM == 3) || SMEM_BYTES + 512 + 1024 <= 233472 / 2, "two CTAs per SM");
-  PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {
-    return ((comp * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
+  PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {  // (one component per pass: comp does not count)
+    return (((NPASS == 1 ? comp : 0) * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
   }
   // word offset of staged slot m (column 0) inside the buffer
   PIC_HD static int slot(int m) { return (m >> 5) * CHUNK_WORDS + (m & 31); }
@@ -199,7 +212,7 @@ __device__ __forceinline__ bool cas_add(double *p, double old, double v) {
 // optimistic compare-and-swap only ever loses against another warp.  (Batches of a whole x-y plane
 // of one component made lanes that own neighbouring cells invalidate each other's old values:
 // about half of the lanes fell back to the spin loop on every entry -- profiles/r1_notes.md.)
-template <int DIM, int ORDER, typename T, class P>
+template <int DIM, int ORDER, typename T, class P, int COMP = -1>
 __device__ __forceinline__ void flush_stencil(const T *acc, T *pj) {
   using G = Tile<DIM, ORDER, T>;
   constexpr int NP = G::NP;
@@ -210,7 +223,8 @@ __device__ __forceinline__ void flush_stencil(const T *acc, T *pj) {
     for (int k2 = 0; k2 < NP; k2++)
 #pragma unroll
       for (int k1 = 0; k1 < NP; k1++) {
-        const bool on[3] = {k1 < NP - 1, k2 < NP - 1, DIM == 2 || k3 < NP - 1};
+        const bool on[3] = {(COMP < 0 || COMP == 0) && k1 < NP - 1, (COMP < 0 || COMP == 1) && k2 < NP - 1,
+                            (COMP < 0 || COMP == 2) && (DIM == 2 || k3 < NP - 1)};
         T *p[3];
         T old[3];
 #pragma unroll
@@ -672,52 +686,85 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               if (he >= nh) break;
               pc = (int)hl[NC * P::HCAP + he];
             }
-            T acc[P::NACC];
-#pragma unroll
-            for (int k = 0; k < P::NACC; k++) acc[k] = T(0);
-            bool halo = !own;
-            while (i < ib || id || halo) {
-              const T *src;
-              int st;
-              if (halo) {      // a piece in a halo cell
-                src = hl + he;
-                st = P::HCAP;
-                halo = false;
-              } else if (i < ib) {  // a trajectory parked in its staged slot
-                src = buf + P::slot(i - pa);
-                st = 32;
-                i++;
-              } else {       // a listed piece
-                src = xl + (id - 1);
-                st = xcap;
-                id = (int)src[NC * st];
+            // one walk over the job's trajectories: all three current components at once, or (3D cubic) one
+            // component per walk, restarting from the same place.  (A macro, not a lambda: as a lambda the
+            // single-pass instantiations came out 0.4 % slower -- profiles/r2_notes.md.)
+#define OSGPU_WALK(COMP)                                                                                      \
+  {                                                                                                           \
+    T acc[P::NACC];                                                                                           \
+    _Pragma("unroll") for (int k = 0; k < P::NACC; k++) acc[k] = T(0);                                        \
+    bool halo = !own;                                                                                         \
+    while (i < ib || id || halo) {                                                                            \
+      const T *src;                                                                                           \
+      int st;                                                                                                 \
+      if (halo) { /* a piece in a halo cell */                                                                \
+        src = hl + he;                                                                                        \
+        st = P::HCAP;                                                                                         \
+        halo = false;                                                                                         \
+      } else if (i < ib) { /* a trajectory parked in its staged slot */                                       \
+        src = buf + P::slot(i - pa);                                                                          \
+        st = 32;                                                                                              \
+        i++;                                                                                                  \
+      } else { /* a listed piece */                                                                           \
+        src = xl + (id - 1);                                                                                  \
+        st = xcap;                                                                                            \
+        id = (int)src[NC * st];                                                                               \
+      }                                                                                                       \
+      Seg<DIM, T> sg;                                                                                         \
+      _Pragma("unroll") for (int d = 0; d < DIM; d++) {                                                       \
+        sg.p0[d] = src[d * st];                                                                               \
+        sg.p1[d] = src[(DIM + d) * st];                                                                       \
+      }                                                                                                       \
+      const T q = src[(DIM + 3) * st];                                                                        \
+      if (DIM == 2) sg.vz = src[(DIM + 2) * st];                                                              \
+      segment_current<DIM, ORDER, T, COMP>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {    \
+        T &r = acc[P::acc_index(comp, k1, k2, k3)];                                                           \
+        r = fmadd(f1, f2, r);                                                                                 \
+      });                                                                                                     \
+    }                                                                                                         \
+    int lc[3];                                                                                                \
+    if (own) {                                                                                                \
+      lc[0] = c % G::TX;                                                                                      \
+      lc[1] = (c / G::TX) % G::TY;                                                                            \
+      lc[2] = c / (G::TX * G::TY);                                                                            \
+    } else {                                                                                                  \
+      _Pragma("unroll") for (int d = 0; d < 3; d++) lc[d] = ((pc >> (5 * d)) & 31) - 1; /* -1..T */           \
+    }                                                                                                         \
+    T *pj = jt + jtile_base<DIM, ORDER, T>(lc);                                                               \
+    flush_stencil<DIM, ORDER, T, P, COMP>(acc, pj);                                                           \
+  }
+            if constexpr (OSGPU_WALK_LAMBDA_FOR(DIM, ORDER)) {
+              [[maybe_unused]] const int i_job = i, id_job = id;
+              auto walk = [&](auto comp_c) {
+                constexpr int COMP = decltype(comp_c)::value;
+                if constexpr (P::NPASS > 1) {
+                  i = i_job;
+                  id = id_job;
+                }
+                OSGPU_WALK(COMP)
+              };
+              if constexpr (P::NPASS == 1) {
+                walk(std::integral_constant<int, -1>{});
+              } else {
+                walk(std::integral_constant<int, 0>{});
+                walk(std::integral_constant<int, 1>{});
+                walk(std::integral_constant<int, 2>{});
               }
-              Seg<DIM, T> sg;
-#pragma unroll
-              for (int d = 0; d < DIM; d++) {
-                sg.p0[d] = src[d * st];
-                sg.p1[d] = src[(DIM + d) * st];
-              }
-              const T q = src[(DIM + 3) * st];
-              if (DIM == 2) sg.vz = src[(DIM + 2) * st];
-              segment_current<DIM, ORDER, T>(sg, q, a.k, [&](int comp, int k1, int k2, int k3, T f1, T f2) {
-                T &r = acc[P::acc_index(comp, k1, k2, k3)];
-                r = fmadd(f1, f2, r);
-              });
-            }
-            int lc[3];
-            if (own) {
-              lc[0] = c % G::TX;
-              lc[1] = (c / G::TX) % G::TY;
-              lc[2] = c / (G::TX * G::TY);
-              own = false;
+            } else if constexpr (P::NPASS == 1) {
+              OSGPU_WALK(-1)
             } else {
-#pragma unroll
-              for (int d = 0; d < 3; d++) lc[d] = ((pc >> (5 * d)) & 31) - 1;  // cell coordinates -1..T
-              he += NTHREADS;
+              const int i_job = i, id_job = id;
+              OSGPU_WALK(0)
+              i = i_job;
+              id = id_job;
+              OSGPU_WALK(1)
+              i = i_job;
+              id = id_job;
+              OSGPU_WALK(2)
             }
-            T *pj = jt + jtile_base<DIM, ORDER, T>(lc);
-            flush_stencil<DIM, ORDER, T, P>(acc, pj);
+#undef OSGPU_WALK
+            if (own) own = false;
+            else he += NTHREADS;
           }
         }
 #if !OSGPU_HALO_JOBS

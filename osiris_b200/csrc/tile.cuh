@@ -384,8 +384,11 @@ PIC_HD T push_one(T *x, T *u, int *l, const T *eb, const PushConst<T> &k, Seg<DI
 // Esirkepov weights of one segment (DEP_CURRENT_2D/3D, simd/os-spec-current-avx2.c:730-865,
 // 1147-1318): calls out(comp, k1, k2, k3, f1, f2) for every non-zero stencil entry, whose value is
 // f1 * f2; the entry belongs to grid point (cell + k + LP) of component comp.
-template <int DIM, int ORDER, typename T, class Out>
+// COMP >= 0 restricts the call to one current component (the weights of the others are never formed):
+// the per-cell register accumulation of the 3D cubic scheme takes one component per pass.
+template <int DIM, int ORDER, typename T, int COMP = -1, class Out>
 PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Out out) {
+  constexpr bool C0 = COMP < 0 || COMP == 0, C1 = COMP < 0 || COMP == 1, C2 = COMP < 0 || COMP == 2;
   constexpr int NP = Stencil<ORDER>::NP;
   {
   T s0[DIM][NP], s1[DIM][NP], wlv[DIM][NP];
@@ -403,14 +406,16 @@ PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Ou
 #pragma unroll
       for (int k1 = 0; k1 < NP; k1++) {
         const T wp2 = s0[0][k1] + s1[0][k1];
-        if (k1 < NP - 1) out(0, k1, k2, 0, wlv[0][k1], wp1);
-        if (k2 < NP - 1) out(1, k1, k2, 0, wlv[1][k2], wp2);
-        const T s00 = s0[0][k1] * s0[1][k2];
-        T tmp1 = fmadd(s1[1][k2], s1[0][k1], s00);
-        const T s10 = s0[0][k1] * s1[1][k2];
-        const T tmp2 = fmadd(s0[1][k2], s1[0][k1], s10);
-        tmp1 = fmadd(tmp2, T(0.5), tmp1);
-        out(2, k1, k2, 0, qvz, tmp1);
+        if (C0 && k1 < NP - 1) out(0, k1, k2, 0, wlv[0][k1], wp1);
+        if (C1 && k2 < NP - 1) out(1, k1, k2, 0, wlv[1][k2], wp2);
+        if (C2) {
+          const T s00 = s0[0][k1] * s0[1][k2];
+          T tmp1 = fmadd(s1[1][k2], s1[0][k1], s00);
+          const T s10 = s0[0][k1] * s1[1][k2];
+          const T tmp2 = fmadd(s0[1][k2], s1[0][k1], s10);
+          tmp1 = fmadd(tmp2, T(0.5), tmp1);
+          out(2, k1, k2, 0, qvz, tmp1);
+        }
       }
     }
   } else {
@@ -442,9 +447,9 @@ PIC_HD void segment_current(const Seg<DIM, T> &a, T q, const PushConst<T> &k, Ou
       for (int k2 = 0; k2 < NP; k2++)
 #pragma unroll
         for (int k1 = 0; k1 < NP; k1++) {
-          if (k1 < NP - 1) out(0, k1, k2, k3, wlv[0][k1], wp1[k3][k2]);
-          if (k2 < NP - 1) out(1, k1, k2, k3, wlv[1][k2], wp2[k3][k1]);
-          if (k3 < NP - 1) out(2, k1, k2, k3, wlv[Z][k3], wp3[k2][k1]);
+          if (C0 && k1 < NP - 1) out(0, k1, k2, k3, wlv[0][k1], wp1[k3][k2]);
+          if (C1 && k2 < NP - 1) out(1, k1, k2, k3, wlv[1][k2], wp2[k3][k1]);
+          if (C2 && k3 < NP - 1) out(2, k1, k2, k3, wlv[Z][k3], wp3[k2][k1]);
         }
   }
 }

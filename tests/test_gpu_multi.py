@@ -52,7 +52,7 @@ def _worker(rank, world, nccl_id, dim, order, prec, node_dims, gnx, nsteps, out_
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("prec", ["f32", "f64"])
 @pytest.mark.parametrize("dim,order,node_dims", [(2, 2, [2, 1]), (2, 1, [1, 2]), (3, 2, [2, 1, 1]), (3, 2, [1, 1, 2]),
-                                                 (3, 2, [2, 2, 1]), (3, 2, [2, 2, 2])])
+                                                 (3, 2, [2, 2, 1]), (3, 2, [2, 2, 2]), (3, 3, [1, 2, 1]), (2, 3, [2, 1])])
 def test_ranks_reproduce_single_gpu(built, tmp_path, dim, order, prec, node_dims):
     world = int(np.prod(node_dims))
     if _ngpu() < world:

@@ -162,11 +162,15 @@ def test_step_phases_match_oracle(built, dim, order, prec):
 
 
 @pytest.mark.parametrize("prec", ["f32", "f64"])
-@pytest.mark.parametrize("dim,order", [(2, 2), (3, 2), (3, 1)])
-def test_n_steps_match_oracle(built, dim, order, prec):
+@pytest.mark.parametrize("dim,order,ppc", [(2, 2, 4), (3, 2, 4), (3, 1, 4), (3, 3, 4), (2, 3, 4),
+                                           # tiles of 256 cells x 10 particles: more than a CTA stages at once
+                                           # (2240 slots in fp32, 1824 for the 3D cubic tiles, ~1000 in fp64), so every
+                                           # tile is pushed and deposited in several pieces
+                                           (3, 2, 10), (3, 3, 10), (2, 3, 10)])
+def test_n_steps_match_oracle(built, dim, order, prec, ppc):
     """N full steps on the device (one osgpu_step call) against N oracle steps"""
-    nsteps = 8
-    sim, ora = _pair(dim, order, prec, SHAPES[dim], ppc=4, seed=7, nspecies=1, umax=0.1)
+    nsteps = 8 if ppc < 10 else 4
+    sim, ora = _pair(dim, order, prec, SHAPES[dim], ppc=ppc, seed=7, nspecies=1, umax=0.1)
     ene = sim.iter(nsteps)
     ene_r = ora.iter(nsteps)
     tol = 2e-4 if prec == "f32" else 1e-9

@@ -166,7 +166,10 @@ def test_step_phases_match_oracle(built, dim, order, prec):
                                            # tiles of 256 cells x 10 particles: more than a CTA stages at once
                                            # (2240 slots in fp32, 1824 for the 3D cubic tiles, ~1000 in fp64), so every
                                            # tile is pushed and deposited in several pieces
-                                           (3, 2, 10), (3, 3, 10), (2, 3, 10)])
+                                           (3, 2, 10), (3, 3, 10), (2, 3, 10),
+                                           # cells that hold more trajectories than one lane walks (np / 128 per
+                                           # piece): the rest of the cell becomes extra jobs of other lanes
+                                           (2, 1, 48), (3, 3, 24), (3, 2, 40)])
 def test_n_steps_match_oracle(built, dim, order, prec, ppc):
     """N full steps on the device (one osgpu_step call) against N oracle steps"""
     nsteps = 8 if ppc < 10 else 4

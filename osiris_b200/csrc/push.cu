@@ -146,6 +146,11 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // deposits directly
   static constexpr bool FAST = ORDER <= 3;
   static constexpr int NPASS = (ORDER == 3 && (DIM == 3 || sizeof(T) == 8)) ? 3 : 1;  // (2D cubic fp64: 40 sums = 80 registers)
+  // 3D cubic fp32: the J tile (22 KB) lives where the E/B tile (27 KB) was -- E/B is dead once a piece is
+  // pushed, J is born when its deposit starts -- which leaves room for 2624 staged particles: a tile of 2048
+  // plus arrivals is pushed and deposited in ONE piece (with both tiles resident it took two, and the second,
+  // ~260 particles in ~30 cells, kept one warp busy while seven waited: 43 % of the samples at CTA barriers)
+  static constexpr bool ALIAS_J = FAST && DIM == 3 && ORDER == 3 && sizeof(T) == 4;
   static constexpr int NWARP = NTHREADS / 32;
   static constexpr int NC = DIM + 4;            // staged columns: x(D) u(3) q, blocked by 32 slots
   static constexpr int CHUNK_WORDS = NC * 32;   // one block of 32 slots
@@ -156,10 +161,9 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // momentum slots hold the end point of the trajectory), above them one region per warp with the
   // list of pieces that belong to other cells of the tile and the queue of particles to split, and
   // at the top the CTA's list of pieces that lie in halo cells
-  // (2 CTAs per SM: the padded 3D quadratic E/B tile takes 2304 B more; the 3D cubic fp32 tiles -- 27 KB of
-  // E/B, 22 KB of J -- leave room for 1824 staged particles, so a tile of 2048 + arrivals takes two pieces)
+  // (2 CTAs per SM: the padded 3D quadratic E/B tile takes 2304 B more; 3D cubic fp32: see ALIAS_J)
   static constexpr int BUF_BYTES = !FAST ? 0
-      : (DIM == 3 && ORDER == 3 && sizeof(T) == 4) ? 60672
+      : ALIAS_J ? 60672 + 22656
       : 74752 - (OSGPU_PAD_EY && DIM == 3 && ORDER == 2 && sizeof(T) == 4 ? 2304 : 0);
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
   static constexpr int XMIN = 20;  // list entries per warp always available
@@ -169,8 +173,9 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static_assert(NROUND <= 16, "one mbarrier (and one phase bit) per staged round");
   static_assert(!FAST || TCAP < 4096, "queue entries keep the slot in 12 bits");
   static constexpr int NACC = (NPASS == 1 ? 3 : 1) * G::NP * G::NP * (DIM == 3 ? G::NP : 1);
-  static constexpr int OFF_JT = 6 * G::ESTRIDE * (int)sizeof(T);
-  static constexpr int OFF_BUF = round_up(OFF_JT + 3 * G::JVOL * (int)sizeof(T), 128);
+  static constexpr int OFF_JT = ALIAS_J ? 0 : 6 * G::ESTRIDE * (int)sizeof(T);
+  static_assert(!ALIAS_J || 3 * G::JVOL <= 6 * G::ESTRIDE, "the J tile fits in the E/B tile's memory");
+  static constexpr int OFF_BUF = round_up((ALIAS_J ? 6 * G::ESTRIDE : 6 * G::ESTRIDE + 3 * G::JVOL) * (int)sizeof(T), 128);
   static constexpr int OFF_CS = OFF_BUF + BUF_BYTES;
   static constexpr int CS_STRIDE = round_up(G::NCELL + 1, 4);
   static constexpr int OFF_HIST = OFF_CS + 2 * CS_STRIDE * 4;
@@ -340,7 +345,8 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     s_arrive = 0;
     s_sortc = 0;
   }
-  for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
+  if constexpr (!P::ALIAS_J)
+    for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
   hist[tid] = 0;
   heads[tid] = 0;
   __syncthreads();
@@ -499,7 +505,26 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
               }
             }
           }
-          if (direct) deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
+          if (direct) {
+            if constexpr (P::ALIAS_J) {
+              // (the shared J tile does not exist during the push: pieces the lists have no room for go to the
+              // grid in global memory, addressed through the J-tile position the statement computes)
+              deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, [&](T *p_, T v) {
+                int org[3];
+                tile_origin(tile, org);
+                const int o_ = (int)(p_ - jt), cc = o_ / G::JVOL;
+                int r_ = o_ - cc * G::JVOL;
+                const int kx = r_ % G::JX; r_ /= G::JX;
+                const int q0 = org[0] + a.g.gl[0] + G::HALO_LO + kx;
+                const int q1 = org[1] + a.g.gl[1] + G::HALO_LO + r_ % G::JY;
+                const int q2 = org[2] + a.g.gl[2] + G::HALO_LO + r_ / G::JY;
+                if (q0 >= 0 && q0 < a.g.S[0] && q1 >= 0 && q1 < a.g.S[1] && q2 >= 0 && q2 < a.g.S[2])
+                  atomicAdd(&a.J[cc][a.g.at(q0, q1, q2)], v);
+              });
+            } else {
+              deposit_segments<DIM, ORDER, T>(seg, nseg, direct, q, jt, a.k, atomic_add);
+            }
+          }
           __syncwarp();
         };
 
@@ -620,6 +645,9 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         if constexpr (P::FAST) pph ^= (1u << nrounds) - 1u;
 
         __syncthreads();  // every warp's trajectories and lists are complete
+        if constexpr (P::ALIAS_J) {  // E/B is dead: its memory becomes the (zeroed) J tile; barriers follow before any flush
+          for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
+        }
 
         if (!more) {
           // all particles of the tile are pushed: new-cell histogram -> cell offsets of the sorted
@@ -794,8 +822,26 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
             s_nx = 0;
             s_pushc = 0;
           }
-          if (P::FAST && tid == 32) stage_particles(off + qa, min(n - qa, P::TCAP));
+          if (P::FAST && tid == 32) {
+            if constexpr (P::ALIAS_J) {  // this piece's J goes out, then E/B comes back for the next piece
+              int org[3];
+              tile_origin(tile, org);
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+              for (int c = 0; c < 3; c++)
+                tma_reduce_add_3d(&maps.m[6 + c], jt + c * G::JVOL, org[0] + a.g.gl[0] + G::HALO_LO,
+                                  org[1] + a.g.gl[1] + G::HALO_LO, org[2] + a.g.gl[2] + G::HALO_LO);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              stage_fields(tile);
+            }
+            stage_particles(off + qa, min(n - qa, P::TCAP));
+          }
           __syncthreads();  // (halo list counter reset before the next piece adds to it)
+          if constexpr (P::ALIAS_J) {
+            mbar_wait(&mbar, phase);
+            phase ^= 1;
+          }
         }
       } while (more);
     }
@@ -830,6 +876,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
           else tma_reduce_add_3d(&maps.m[6 + c], jt + c * G::JVOL, c0, c1, c2);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if constexpr (P::ALIAS_J) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // J is read before E/B lands on it
       }
       if (s_next[0] < a.tl.ntile) {
         stage_fields(s_next[0]);
@@ -939,7 +986,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
         }
         jt[i] = T(0);
       }
-    } else {
+    } else if constexpr (!P::ALIAS_J) {
       for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) jt[i] = T(0);
     }
     hist[tid] = 0;

@@ -164,6 +164,9 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // (2 CTAs per SM: the padded 3D quadratic E/B tile takes 2304 B more; 3D cubic fp32: see ALIAS_J)
   static constexpr int BUF_BYTES = !FAST ? 0
       : ALIAS_J ? 60672 + 22656
+      // 3D fp64 runs one CTA per SM (255 registers per thread): the whole 227 KB are its own, enough to stage a
+      // tile of 2048 + arrivals in one piece (with the two-CTA buffer a tile took two to three pieces)
+      : (DIM == 3 && sizeof(T) == 8) ? (ORDER == 3 ? 127616 : 143872)
       : 74752 - (OSGPU_PAD_EY && DIM == 3 && ORDER == 2 && sizeof(T) == 4 ? 2304 : 0);
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
   static constexpr int XMIN = 20;  // list entries per warp always available
@@ -186,6 +189,7 @@ template <int DIM, int ORDER, typename T> struct Plan {
   // all instantiations but 3D fp64 are meant to run two CTAs per SM: 233472 bytes per SM, 1024 reserved
   // per CTA, < 512 bytes of static shared variables in the kernel
   static_assert((sizeof(T) == 8 && DIM == 3) || SMEM_BYTES + 512 + 1024 <= 233472 / 2, "two CTAs per SM");
+  static_assert(SMEM_BYTES + 512 <= 232448, "dynamic shared memory of one CTA");
   PIC_HD static int acc_index(int comp, int k1, int k2, int k3) {  // (one component per pass: comp does not count)
     return (((NPASS == 1 ? comp : 0) * (DIM == 3 ? G::NP : 1) + k3) * G::NP + k2) * G::NP + k1;
   }

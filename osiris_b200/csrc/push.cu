@@ -42,6 +42,9 @@ using namespace pic;
 #ifndef OSGPU_WALK_LAMBDA_FOR
 #define OSGPU_WALK_LAMBDA_FOR(DIM, ORDER) ((DIM) == 2 || (ORDER) == 3)
 #endif
+#ifndef OSGPU_BUF2D
+#define OSGPU_BUF2D 94208
+#endif
 #ifndef OSGPU_HALO_JOBS
 #define OSGPU_HALO_JOBS 1
 #endif
@@ -167,6 +170,9 @@ template <int DIM, int ORDER, typename T> struct Plan {
       // 3D fp64 runs one CTA per SM (255 registers per thread): the whole 227 KB are its own, enough to stage a
       // tile of 2048 + arrivals in one piece (with the two-CTA buffer a tile took two to three pieces)
       : (DIM == 3 && sizeof(T) == 8) ? (ORDER == 3 ? 127616 : 143872)
+      // 2D fp32: the tiles are small (E/B + J < 17 KB), the buffer takes what two CTAs per SM leave: 3600 slots
+      // instead of 2784 (64 particles per cell fill a 256-cell tile with 16384: five pieces instead of six)
+      : (DIM == 2 && sizeof(T) == 4) ? OSGPU_BUF2D
       : 74752 - (OSGPU_PAD_EY && DIM == 3 && ORDER == 2 && sizeof(T) == 4 ? 2304 : 0);
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
   static constexpr int XMIN = 20;  // list entries per warp always available

@@ -42,6 +42,9 @@ using namespace pic;
 #ifndef OSGPU_WALK_LAMBDA_FOR
 #define OSGPU_WALK_LAMBDA_FOR(DIM, ORDER) ((DIM) == 2 || (ORDER) == 3)
 #endif
+#ifndef OSGPU_BUF3D64
+#define OSGPU_BUF3D64 151680
+#endif
 #ifndef OSGPU_BUF2D
 #define OSGPU_BUF2D 94208
 #endif
@@ -169,7 +172,7 @@ template <int DIM, int ORDER, typename T> struct Plan {
       : ALIAS_J ? 60672 + 22656
       // 3D fp64 runs one CTA per SM (255 registers per thread): the whole 227 KB are its own, enough to stage a
       // tile of 2048 + arrivals in one piece (with the two-CTA buffer a tile took two to three pieces)
-      : (DIM == 3 && sizeof(T) == 8) ? (ORDER == 3 ? 127616 : 143872)
+      : (DIM == 3 && sizeof(T) == 8) ? (ORDER == 3 ? 127616 : OSGPU_BUF3D64)
       // 2D fp32: the tiles are small (E/B + J < 17 KB), the buffer takes what two CTAs per SM leave: 3600 slots
       // instead of 2784 (64 particles per cell fill a 256-cell tile with 16384: five pieces instead of six)
       : (DIM == 2 && sizeof(T) == 4) ? OSGPU_BUF2D
@@ -177,7 +180,10 @@ template <int DIM, int ORDER, typename T> struct Plan {
   static constexpr int BUF_WORDS = BUF_BYTES / (int)sizeof(T);
   static constexpr int XMIN = 20;  // list entries per warp always available
   static constexpr int HCAP = OSGPU_PAD_EY ? 64 : 96;  // CTA-wide list of pieces in halo cells (top of the buffer)
-  static constexpr int TCAP = FAST ? (((BUF_WORDS - NWARP * (XMIN * XW + QWORDS) - HCAP * XW) / NC) & ~31) : (1 << 30);
+  // (ALIAS_J: at most 2400 of the 2624 slots that fit, so that a full piece still leaves its crossers' pieces
+  // ~400 list entries instead of 180 and they do not end up on the global-memory path)
+  static constexpr int TCAP_FIT = ((BUF_WORDS - NWARP * (XMIN * XW + QWORDS) - HCAP * XW) / NC) & ~31;
+  static constexpr int TCAP = FAST ? (ALIAS_J && TCAP_FIT > 2400 ? 2400 : TCAP_FIT) : (1 << 30);
   static constexpr int NROUND = FAST ? (TCAP + NTHREADS - 1) / NTHREADS : 1;
   static_assert(NROUND <= 16, "one mbarrier (and one phase bit) per staged round");
   static_assert(!FAST || TCAP < 4096, "queue entries keep the slot in 12 bits");

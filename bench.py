@@ -288,7 +288,8 @@ def main():
         sim.sync()
 
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:  # (rank 0 prints the line; seven more nvidia-smi loops would only load the host)
+        sampler.start()
     sim.iter(args.settle)
     sim.iter(warmup)
     barrier()

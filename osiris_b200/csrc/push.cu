@@ -33,9 +33,6 @@ namespace osgpu {
 
 using namespace pic;
 
-#ifndef OSGPU_LATE_STAGE
-#define OSGPU_LATE_STAGE 0
-#endif
 // the per-cell walk of the deposit as a lambda (1) or expanded in place (0), per dimensionality: the
 // same statements, different register allocation -- measured per case (profiles/r2_notes.md)
 // (same box: 2D linear 2.32 -> 2.19 ms and 3D cubic 7.44 -> 7.16 ms as a lambda, 3D quadratic 12.19 -> 12.22)
@@ -896,9 +893,7 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
       }
       if (s_next[0] < a.tl.ntile) {
         stage_fields(s_next[0]);
-#if !OSGPU_LATE_STAGE
         if (P::FAST) stage_particles(s_next_off, min(s_next[1], P::TCAP));
-#endif
       }
     }
 
@@ -982,9 +977,6 @@ __global__ void __launch_bounds__(NTHREADS, (sizeof(T) == 8 && DIM == 3) ? 1 : 2
     }
     if (P::TMA_J && last) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();  // sort done (offsets in hist free), every warp's deposit done, J tile read by the TMA
-#if OSGPU_LATE_STAGE
-    if (P::FAST && tid == 32 && s_next[0] < a.tl.ntile) stage_particles(s_next_off, min(s_next[1], P::TCAP));
-#endif
     if constexpr (!P::TMA_J) {
       for (int i = tid; i < 3 * G::JVOL; i += NTHREADS) {
         const T v = jt[i];

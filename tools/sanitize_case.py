@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from osiris_b200.loads import lattice_species  # noqa: E402
 from osiris_b200.simulation import Simulation  # noqa: E402
 
-cases = [(3, 2, "f32", [24, 16, 12], [2, 2, 2]), (2, 3, "f64", [40, 24], [3, 3]), (3, 1, "f32", [16, 16, 8], [2, 1, 2])]
+cases = [(3, 2, "f32", [24, 16, 12], [2, 2, 2]), (3, 3, "f32", [16, 16, 8], [3, 2, 2]),   # cubic: J tile on the E/B tile's memory, 3072 per tile: two pieces
+         (2, 3, "f64", [40, 24], [3, 3]), (3, 1, "f32", [16, 16, 8], [2, 1, 2]), (2, 1, "f32", [32, 32], [6, 6])]
 if len(sys.argv) > 1:
     cases = cases[:int(sys.argv[1])]
 for dim, order, prec, nx, ppc in cases:

@@ -24,6 +24,11 @@
 //   5. exclusive scan of the histogram -> cell offsets; scratch -> particle buffer at
 //      offset[new cell] + rank (the tile is sorted by cell again); particles that left the tile go
 //      to the species' mover buffer.
+// Spline orders 1-3 take this path (struct Plan).  The 3D cubic stencil (3 x 48 sums) is accumulated
+// one current component per walk over the cell's trajectories, and its J tile reuses the E/B tile's
+// shared memory once the push is over (Plan::ALIAS_J), so that a tile of 2048 particles is staged at
+// once; a tile with more particles than the staging buffer holds is processed in pieces.  Order 4
+// loads its particles from global memory and adds every trajectory piece to the J tile directly.
 #include <cuda.h>
 
 #include "common.cuh"

@@ -231,15 +231,15 @@ int osgpu_species_deposit_charge(osgpu_sim *sim, int sp_id, void *rho, int accum
 /* One phasespace of the species' diagnostics (spec/diagnostics/os-spec-phasespace.f03), deposited on the
  * device: the axes and the deposited quantity are the reference's own codes. */
 typedef struct osgpu_phasespace {
-  int32_t ndims;       /* 1 | 2 (save_phasespace_1D :970-1067, save_phasespace_2D :1071-1169)                  */
-  int32_t x_or_p[2];   /* axis quantity: 1 x, 2 p, 3 gamma, 4 log10 gamma, 5 l (angular momentum), 6 log10 ke  */
+  int32_t ndims;       /* 1 | 2 | 3 (save_phasespace_1D :970-1067, _2D :1071-1169, _3D :1173-1276)             */
+  int32_t x_or_p[3];   /* axis quantity: 1 x, 2 p, 3 gamma, 4 log10 gamma, 5 l (angular momentum), 6 log10 ke  */
                        /* (p_phase_x .. p_phase_kel :28-33; get_phasespace_axis_spec :3196-3238, get_l :314)   */
-  int32_t xp_dim[2];   /* component 1..3 of x, p or l (ignored for gamma, log_gamma, log_ke)                    */
+  int32_t xp_dim[3];   /* component 1..3 of x, p or l (ignored for gamma, log_gamma, log_ke)                    */
   int32_t ps_type;     /* deposited quantity: 0 charge, 1 mass, 2 ene, 3-5 q1..q3, 6 |charge|, 7-9 j1..j3       */
                        /* (p_pstype_normal .. p_pstype_j3 :37-46; get_phasespace_charge :2627-2737)            */
-  int32_t n[2];        /* grid points per axis                                                                   */
+  int32_t n[3];        /* grid points per axis                                                                   */
   int32_t use_ene_bin; /* != 0: only particles with ene_bin[0] < u^2/(gamma+1) <= ene_bin[1] count (:2726-2735) */
-  double min[2], max[2]; /* axis range (params%min / %max)                                                       */
+  double min[3], max[3]; /* axis range (params%min / %max)                                                       */
   double ene_bin[2];
   /* get_position (spec/os-spec-define.f03:1098-1150): pos = xmin + dx * ((ix + ixmin) + x) with
    * xmin = g_box(p_lower, comp), ixmin = my_nx_p(1, comp) - 2; center = middle of g_box (get_l :335) */
@@ -247,8 +247,8 @@ typedef struct osgpu_phasespace {
   int32_t ixmin[OSGPU_MAX_DIM];
 } osgpu_phasespace;
 /* replaces: the particle loop of save_phasespace_1D / _2D -- get_phasespace_axis, get_phasespace_charge,
- * deposit_1D / deposit_2D (:1633-1775: linear weighting onto the two nearest grid points per axis, points
- * outside 1..n dropped) -- over the species on this rank.  buffer: n[0] (* n[1]) values of p_diag_prec (single,
+ * deposit_1D / _2D / _3D (:1633-1902: linear weighting onto the two nearest grid points per axis, points
+ * outside 1..n dropped) -- over the species on this rank.  buffer: n[0] (* n[1] (* n[2])) values of p_diag_prec (single,
  * dutil/os-dutil.f03:26), ADDED to when accumulate != 0, otherwise overwritten.  The sum over ranks
  * (reduce_array_size) and normalize_1D / _2D stay with the host. */
 int osgpu_species_phasespace(osgpu_sim *sim, int sp_id, const osgpu_phasespace *ps, float *buffer, int accumulate);

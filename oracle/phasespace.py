@@ -6,14 +6,14 @@ spec/diagnostics/os-spec-phasespace.f03, statement by statement and in the refer
   * get_l               os-spec-phasespace.f03:314-409
   * axis quantity       get_phasespace_axis_spec :3196-3238
   * deposited quantity  get_phasespace_charge :2627-2737
-  * deposit_1D :1633-1689, deposit_2D :1693-1775
+  * deposit_1D :1633-1689, deposit_2D :1693-1775, deposit_3D :1779-1902
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import this module.  Parity unpinned by a
 reference binary (Fortran, not compilable here) and the reference holds no golden vector for it: pinned by the
 invariants of tests/test_phasespace_cpu.py (total deposited quantity, first moment, hand-computed cases).
 
 Particles are ix[np, dim] (1-based local cell), x[np, dim], p[np, 3], q[np]; the phasespace is returned as a
-float32 array [n2, n1] (first axis fastest, the reference's buffer order) or [n1].
+float32 array [(n3,) n2, n1] (first axis fastest, the reference's buffer order) or [n1].
 """
 import numpy as np
 
@@ -94,7 +94,7 @@ def quantity(ps_type, p, q, rqm, ene_bin=None):
 
 
 def deposit(axes_values, lq, n, lo, hi, T, buffer=None):
-    """deposit_1D / deposit_2D with ixmin = 1, ixmax = n (the whole phasespace on this rank).  The sums run
+    """deposit_1D / _2D / _3D with ixmin = 1, ixmax = n (the whole phasespace on this rank).  The sums run
     in particle order like the reference's loop (float32 accumulation), so this is O(np) python: small cases."""
     nd = len(axes_values)
     buf = np.zeros(tuple(reversed(n[:nd])), F) if buffer is None else buffer
@@ -113,7 +113,7 @@ def deposit(axes_values, lq, n, lo, hi, T, buffer=None):
                 buf[i - 1] += (one - eps[0][l]) * lq[l]
             if 1 <= i + 1 <= n[0]:
                 buf[i] += eps[0][l] * lq[l]
-        else:
+        elif nd == 2:
             i, j = int(idx[0][l]), int(idx[1][l])
             e1, e2 = eps[0][l], eps[1][l]
             if 1 <= j <= n[1]:
@@ -126,6 +126,19 @@ def deposit(axes_values, lq, n, lo, hi, T, buffer=None):
                     buf[j, i - 1] += (one - e1) * e2 * lq[l]
                 if 1 <= i + 1 <= n[0]:
                     buf[j, i] += e1 * e2 * lq[l]
+        else:  # deposit_3D (:1779-1902)
+            i, j, k = int(idx[0][l]), int(idx[1][l]), int(idx[2][l])
+            e1, e2, e3 = eps[0][l], eps[1][l], eps[2][l]
+            for kk, w3 in ((k, one - e3), (k + 1, e3)):
+                if not 1 <= kk <= n[2]:
+                    continue
+                for jj, w2 in ((j, one - e2), (j + 1, e2)):
+                    if not 1 <= jj <= n[1]:
+                        continue
+                    if 1 <= i <= n[0]:
+                        buf[kk - 1, jj - 1, i - 1] += (one - e1) * w2 * w3 * lq[l]
+                    if 1 <= i + 1 <= n[0]:
+                        buf[kk - 1, jj - 1, i] += e1 * w2 * w3 * lq[l]
     return buf
 
 

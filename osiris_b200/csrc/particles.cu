@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(256)
   o0[1] = (t % tl.nt[1]) * tl.T[1]; t /= tl.nt[1];
   o0[2] = t * tl.T[2];
   const int nd = a.ps.ndims;
-  T rdx[2] = {T(0), T(0)};
+  T rdx[3] = {T(0), T(0), T(0)};
   for (int k = 0; k < nd; k++) rdx[k] = (T)a.ps.n[k] / ((T)a.ps.max[k] - (T)a.ps.min[k]);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const long long s = off + i;
@@ -574,26 +574,30 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int d = 0; d < 3; d++) p[d] = sp.r(DIM + d, s);
     const float lq = phase_quantity<T>(a, sp.r(DIM + 3, s), p);
-    // deposit_1D / deposit_2D (:1633-1775): nearest point and the one above it, linear weights
-    int i1[2] = {1, 1};
-    float eps[2] = {0.0f, 0.0f};
+    // deposit_1D / _2D / _3D (:1633-1902): nearest point and the one above it along every axis, linear
+    // weights multiplied in the reference's order ((w1 * w2) * w3) * q
+    int i1[3] = {1, 1, 1};
+    float eps[3] = {0.0f, 0.0f, 0.0f};
     for (int k = 0; k < nd; k++) {
       const T nx1 = ((T)phase_axis<DIM, T>(a, k, ix, x, p) - (T)a.ps.min[k]) * rdx[k];
       i1[k] = (int)lrint(round((double)nx1));  // nint: halves away from zero
       eps[k] = (float)(nx1 - (T)i1[k]) + 0.5f;
     }
-    const int n1 = a.ps.n[0];
-    if (nd == 1) {
-      if (i1[0] >= 1 && i1[0] <= n1) atomicAdd(&buf[i1[0] - 1], (1.0f - eps[0]) * lq);
-      if (i1[0] + 1 >= 1 && i1[0] + 1 <= n1) atomicAdd(&buf[i1[0]], eps[0] * lq);
-    } else {
-      for (int b2 = 0; b2 < 2; b2++) {
-        const int j2 = i1[1] + b2;
-        if (j2 < 1 || j2 > a.ps.n[1]) continue;
-        const float w2 = b2 ? eps[1] : 1.0f - eps[1];
-        float *row = buf + (long long)(j2 - 1) * n1;
-        if (i1[0] >= 1 && i1[0] <= n1) atomicAdd(&row[i1[0] - 1], ((1.0f - eps[0]) * w2) * lq);
-        if (i1[0] + 1 >= 1 && i1[0] + 1 <= n1) atomicAdd(&row[i1[0]], (eps[0] * w2) * lq);
+    const int n1 = a.ps.n[0], n2 = nd > 1 ? a.ps.n[1] : 1, n3 = nd > 2 ? a.ps.n[2] : 1;
+    for (int b3 = 0; b3 < (nd > 2 ? 2 : 1); b3++) {
+      const int j3 = nd > 2 ? i1[2] + b3 : 1;
+      if (j3 < 1 || j3 > n3) continue;
+      for (int b2 = 0; b2 < (nd > 1 ? 2 : 1); b2++) {
+        const int j2 = nd > 1 ? i1[1] + b2 : 1;
+        if (j2 < 1 || j2 > n2) continue;
+        for (int b1 = 0; b1 < 2; b1++) {
+          const int j1 = i1[0] + b1;
+          if (j1 < 1 || j1 > n1) continue;
+          float w = b1 ? eps[0] : 1.0f - eps[0];
+          if (nd > 1) w = w * (b2 ? eps[1] : 1.0f - eps[1]);
+          if (nd > 2) w = w * (b3 ? eps[2] : 1.0f - eps[2]);
+          atomicAdd(&buf[(j1 - 1) + (long long)n1 * ((j2 - 1) + (long long)n2 * (j3 - 1))], w * lq);
+        }
       }
     }
   }

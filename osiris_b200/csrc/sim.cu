@@ -1216,7 +1216,7 @@ template <typename T> struct Sim final : SimBase {
     }
     return OSGPU_OK;
   }
-  // The particle loop of save_phasespace_1D / _2D (spec/diagnostics/os-spec-phasespace.f03:970-1169) for the
+  // The particle loop of save_phasespace_1D / _2D / _3D (spec/diagnostics/os-spec-phasespace.f03:970-1276) for the
   // particles of this rank.  Refused between move_window and the next push while the species holds guests
   // of the trailing wall (the reference takes its diagnostics before the window moves, os-main.f03).
   float *ps_buf = nullptr;
@@ -1226,7 +1226,7 @@ template <typename T> struct Sim final : SimBase {
     Species &s = sp[id];
     if (s.movers_pending) { set_error("phasespace: species %d has unprocessed leavers (call update_boundary first)", id); return OSGPU_ERR_INVALID; }
     if (s.guests_pending) { set_error("phasespace: species %d holds window guests between move_window and push", id); return OSGPU_ERR_INVALID; }
-    if (ps->ndims < 1 || ps->ndims > 2) { set_error("phasespace: ndims = %d (1 or 2; 3D phasespaces are not built)", ps->ndims); return OSGPU_ERR_INVALID; }
+    if (ps->ndims < 1 || ps->ndims > 3) { set_error("phasespace: ndims = %d outside 1..3", ps->ndims); return OSGPU_ERR_INVALID; }
     if (ps->ps_type < 0 || ps->ps_type > 9) { set_error("phasespace: ps_type = %d", ps->ps_type); return OSGPU_ERR_INVALID; }
     size_t cells = 1;
     for (int k = 0; k < ps->ndims; k++) {

@@ -37,9 +37,9 @@ class Config(C.Structure):
 class Phasespace(C.Structure):
     """osgpu_phasespace (include/osiris_b200.h)"""
     _fields_ = [
-        ("ndims", C.c_int32), ("x_or_p", C.c_int32 * 2), ("xp_dim", C.c_int32 * 2), ("ps_type", C.c_int32),
-        ("n", C.c_int32 * 2), ("use_ene_bin", C.c_int32),
-        ("min", C.c_double * 2), ("max", C.c_double * 2), ("ene_bin", C.c_double * 2),
+        ("ndims", C.c_int32), ("x_or_p", C.c_int32 * 3), ("xp_dim", C.c_int32 * 3), ("ps_type", C.c_int32),
+        ("n", C.c_int32 * 3), ("use_ene_bin", C.c_int32),
+        ("min", C.c_double * 3), ("max", C.c_double * 3), ("ene_bin", C.c_double * 2),
         ("xmin", C.c_double * 3), ("center", C.c_double * 3), ("ixmin", C.c_int32 * 3),
     ]
 

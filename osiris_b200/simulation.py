@@ -226,11 +226,11 @@ class Species:
 
     def phasespace(self, axes, n, lo, hi, ps_type="charge", ene_bin=None, g_box=None, my_nx_p_lo=None,
                    buffer=None):
-        """The particle loop of save_phasespace_1D / _2D (os-spec-phasespace.f03:970-1169): deposit this
-        rank's particles of the species on the phasespace grid.  axes: one or two of ("x", 1), ("p", 2),
+        """The particle loop of save_phasespace_1D / _2D / _3D (os-spec-phasespace.f03:970-1276): deposit this
+        rank's particles of the species on the phasespace grid.  axes: one to three of ("x", 1), ("p", 2),
         ("g", 0), ("gl", 0), ("l", 3), ("kel", 0), FIRST axis first; n, lo, hi: points and range per axis.
         g_box ([lower], [upper]) and my_nx_p_lo (global index of this rank's first cell, 1-based) default to
-        a box starting at 0 split evenly over the nodes.  Returns float32 [n2, n1] (or [n1]); buffer, when
+        a box starting at 0 split evenly over the nodes.  Returns float32 [(n3,) n2, n1] (or [n1]); buffer, when
         given, is added to.  The sum over ranks and the normalisation stay with the caller."""
         sim = self.sim
         ps = _lib.Phasespace()

@@ -80,6 +80,8 @@ PHASESPACES = [
     ([("l", 3), ("p", 1)], [18, 12], [-8.0, -3.0], [8.0, 3.0]),
     ([("l", 1)], [21], [-6.0], [6.0]),
     ([("l", 2), ("g", 0)], [15, 9], [-6.0, 1.0], [6.0, 3.5]),
+    ([("p", 1), ("p", 2), ("p", 3)], [10, 8, 6], [-3.0, -3.0, -3.0], [3.0, 3.0, 3.0]),   # p3p2p1 (deposit_3D)
+    ([("x", 1), ("x", 2), ("p", 1)], [12, 9, 7], [0.0, 0.5, -2.5], None),                # p1x2x1, partly outside
 ]
 
 

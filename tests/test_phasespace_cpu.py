@@ -78,3 +78,25 @@ def test_invariants(dim, prec):
     l1 = r[1] * u[:, 2] - (r[2] * u[:, 1] if dim == 3 else 0.0)
     got = ph.axis_value("l", 1, *args[:4], g_box, dx, lo_)
     assert np.abs(got - l1).max() < 1e-5 * max(1.0, np.abs(l1).max())
+
+
+def test_three_axes():
+    """deposit_3D: the total is the particle sum, every marginal is the 2D (and 1D) phasespace of the same axes"""
+    c = random_case(3, 2, "f32", [8, 6, 6], ppc=3, seed=9)
+    dx = [0.5] * 3
+    g_box = ([0.0] * 3, [4.0, 3.0, 3.0])
+    args = (3, c["ix"], c["x"], c["u"], c["q"], -1.0, g_box, dx, [1, 1, 1])
+    axes, n, lo, hi = [("x", 1), ("p", 1), ("p", 2)], [10, 8, 6], [-1.0, -4.0, -4.0], [5.0, 4.0, 4.0]
+    out = ph.phasespace(axes, n, lo, hi, *args)
+    assert out.shape == (6, 8, 10)
+    assert out.sum(dtype=np.float64) == pytest.approx(c["q"].sum(dtype=np.float64), rel=1e-5)
+    two = ph.phasespace(axes[:2], n[:2], lo[:2], hi[:2], *args)
+    assert np.abs(out.sum(axis=0, dtype=np.float64) - two).max() < 1e-4 * np.abs(two).max()
+    one = ph.phasespace(axes[2:], n[2:], lo[2:], hi[2:], *args)
+    assert np.abs(out.sum(axis=(1, 2), dtype=np.float64) - one).max() < 1e-4 * np.abs(one).max()
+    # a particle in the middle of a point: that point alone
+    ix, x, p, q = (np.array([[3, 1, 1]], np.int32), np.array([[0.25, 0.0, 0.0]], np.float32),
+                   np.array([[0.5, -0.5, 0.0]], np.float32), np.array([2.0], np.float32))
+    o = ph.phasespace([("p", 1), ("p", 2), ("p", 3)], [4, 4, 4], [-2.0] * 3, [2.0] * 3, 3, ix, x, p, q, -1.0, g_box, dx, [1, 1, 1])
+    # p = (0.5, -0.5, 0): nx = (2.5, 1.5, 2.0) -> i = (3, 2, 2), eps = (0, 0, 0.5): half on k = 2, half on k = 3
+    assert o[1, 1, 2] == 1.0 and o[2, 1, 2] == 1.0 and o.sum() == 2.0
